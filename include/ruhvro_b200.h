@@ -1,0 +1,127 @@
+/*
+ * ruhvro_b200.h — C ABI of the B200-native Avro -> Arrow direct decoder.
+ *
+ * This is the drop-in boundary for the reference's direct-decode hot path: every entry
+ * point names the reference interface it replaces (file:line in Tyler-Sch/pyruhvro @ de4683de).
+ * A Rust `extern "C"` shim inside `ruhvro::deserialize` (or the ctypes/CPython binding in
+ * pyruhvro_b200/) binds these 1:1 — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no C++/torch types.  All functions are thread-safe and
+ *     never throw or abort across the boundary.
+ *   - Status 0 = success; non-zero = the error category below.  rv_last_error() returns the
+ *     calling thread's last message (the analogue of the reference's anyhow::Error string,
+ *     surfaced to Python as ValueError at src/lib.rs:25-27).
+ *   - Inputs are borrowed for the duration of the call.  Outputs are owned by the library and
+ *     released through rv_result_free() and the Arrow C Data Interface release callbacks.
+ *   - There is NO CPU fallback: schemas outside the direct-decode subset
+ *     (fast_decode.rs:38-61) are an error here, where the reference would drop to its
+ *     Value-tree path (deserialize.rs:26-29).  A missing CUDA device is an error.
+ */
+#ifndef RUHVRO_B200_H
+#define RUHVRO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct ArrowSchema;      /* Arrow C Data Interface (pyruhvro_b200/csrc/arrow_c.h) */
+struct ArrowArray;
+struct ArrowDeviceArray; /* Arrow C Device Data Interface */
+
+typedef struct rv_schema rv_schema; /* parsed Avro schema + decode plan; immutable, ref-counted */
+typedef struct rv_result rv_result; /* the k RecordBatches of one decode call */
+
+typedef enum rv_status {
+    RV_OK = 0,
+    /* data errors: categories of the reference's bail!/anyhow! sites in fast_decode.rs */
+    RV_ERR_EOF = 1,          /* :849,874,884,910 "unexpected end of buffer" */
+    RV_ERR_VARINT = 2,       /* :866 "zigzag varint too long" */
+    RV_ERR_BOOL = 3,         /* :898 "invalid boolean byte" */
+    RV_ERR_NEG_LEN = 4,      /* :906 "negative string length" */
+    RV_ERR_BRANCH = 5,       /* :591,646 union branch index invalid / out of range */
+    RV_ERR_ENUM = 6,         /* :575 "enum index out of range" */
+    RV_ERR_SCHEMA = 7,       /* schema does not parse / outside the supported subset / over a documented limit */
+    RV_ERR_OVERFLOW = 8,     /* a column of one batch exceeds Arrow's i32 offsets (arrow-rs panics here) */
+    RV_ERR_INVALID = 9,      /* bad argument */
+    RV_ERR_CUDA = 10         /* CUDA runtime failure (includes "no device") */
+} rv_status;
+
+/* ---- schema --------------------------------------------------------------------------- */
+
+/* Replaces ruhvro::deserialize::parse_schema (ruhvro/src/deserialize.rs:18-20).  Parsing an
+ * unsupported-but-valid schema succeeds; use rv_schema_is_supported() for the gate. */
+rv_status rv_schema_parse(const char* json, size_t len, rv_schema** out);
+rv_schema* rv_schema_retain(rv_schema* s);  /* Arc::clone (deserialize.rs:96) */
+void rv_schema_release(rv_schema* s);
+
+/* Replaces fast_decode::is_supported (ruhvro/src/fast_decode.rs:38-61): 1 = decodable here. */
+int rv_schema_is_supported(const rv_schema* s);
+
+/* Replaces schema_translate::to_arrow_schema (ruhvro/src/schema_translate.rs:19-37): exports
+ * the Arrow schema ("+s" struct of the top-level fields) of the batches decode returns. */
+rv_status rv_schema_export_arrow(const rv_schema* s, struct ArrowSchema* out);
+
+/* ---- decode ---------------------------------------------------------------------------- */
+
+/* Replaces ruhvro::deserialize::per_datum_deserialize_threaded (ruhvro/src/deserialize.rs:76-121)
+ * and, with num_chunks = 1, per_datum_deserialize (:25-30).
+ *
+ * `data`/`offsets` are the packed form the reference itself builds with BinaryArray::from_vec
+ * (:90): record i is data[offsets[i] .. offsets[i+1]), offsets has n+1 entries (i64, so inputs
+ * beyond 2 GiB are addressable).  num_chunks is clamped like clamp_chunks (:53-55) and rows are
+ * partitioned like build_slices (:57-68): chunk = n / k, the last chunk takes the remainder;
+ * one RecordBatch per chunk, in order.  n = 0 yields one empty batch.
+ *
+ * Host variant: `data`/`offsets` are host memory (pinned memory from rv_host_alloc gives full
+ * PCIe bandwidth); the batches' buffers land in library-owned pinned host memory. */
+rv_status rv_decode_host(const rv_schema* s, const uint8_t* data, const int64_t* offsets, int64_t n,
+                         int64_t num_chunks, rv_result** out);
+
+/* Device variant (the benchmark / pipeline path): `d_data`/`d_offsets` are device pointers on the
+ * current CUDA device, `d_data` 16-byte aligned; work is enqueued on `cuda_stream` (a
+ * cudaStream_t; NULL = default stream) and the call returns after the kernels completed.  The
+ * batches stay in HBM until rv_result_to_host(). */
+rv_status rv_decode_device(const rv_schema* s, const uint8_t* d_data, const int64_t* d_offsets, int64_t n,
+                           int64_t num_chunks, void* cuda_stream, rv_result** out);
+
+/* Copies a device-resident result's buffers to pinned host memory (no-op if already there). */
+rv_status rv_result_to_host(rv_result* r);
+
+int64_t rv_result_num_batches(const rv_result* r);
+int64_t rv_result_num_rows(const rv_result* r, int64_t batch);
+/* Exact bytes of every Arrow buffer that is exported (the B_out of the roofline bookkeeping). */
+int64_t rv_result_arrow_bytes(const rv_result* r);
+
+/* Exports batch i as a struct array + (optionally, may be NULL) its schema through the Arrow C
+ * Data Interface — what PyArrowType<RecordBatch> does at src/lib.rs:70,88.  Requires host buffers.
+ * The exported array keeps the result's memory alive until its release callback runs. */
+rv_status rv_result_export(rv_result* r, int64_t batch, struct ArrowArray* out_array, struct ArrowSchema* out_schema);
+/* Same, for a device-resident result (device_type = ARROW_DEVICE_CUDA, buffers are device pointers). */
+rv_status rv_result_export_device(rv_result* r, int64_t batch, struct ArrowDeviceArray* out_array, struct ArrowSchema* out_schema);
+
+void rv_result_free(rv_result* r);
+
+/* ---- memory / introspection ------------------------------------------------------------- */
+
+void* rv_host_alloc(size_t bytes); /* pinned host memory (cudaHostAlloc); NULL on failure */
+void rv_host_free(void* p);
+
+/* Per-call kernel timings of the calling thread's last decode, in milliseconds (CUDA events on
+ * the launch stream): [0] count_kernel, [1] scan_kernel, [2] emit_kernel, [3] null_count_kernel,
+ * [4] H2D copy, [5] D2H copy.  Returns how many entries were written (<= cap). */
+int rv_last_timings(float* out_ms, int cap);
+/* Number of kernels the last decode on this thread launched. */
+int rv_last_launch_count(void);
+
+const char* rv_last_error(void);
+const char* rv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RUHVRO_B200_H */

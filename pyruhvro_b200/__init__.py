@@ -1,0 +1,213 @@
+"""pyruhvro_b200 — B200-native drop-in for pyruhvro's direct Avro→Arrow decode path.
+
+Python surface mirrored from the reference's PyO3 module (``/root/reference/src/lib.rs``):
+
+    deserialize_array(list, schema)                          -> pyarrow.RecordBatch        (:56-71)
+    deserialize_array_threaded(list, schema, num_chunks)     -> list[pyarrow.RecordBatch]  (:73-89)
+    deserialize_array_threaded_spawn(list, schema, chunks)   -> list[pyarrow.RecordBatch]  (:108-128)
+    serialize_record_batch(batch, schema, num_chunks)        -> list[pyarrow.Array]        (:91-106)
+    serialize_record_batch_spawn(batch, schema, num_chunks)  -> list[pyarrow.Array]        (:130-147)
+
+Same argument meaning and error behaviour: elements of ``list`` must be ``bytes``; every failure is
+a ``ValueError`` carrying the native message (:25-27); the GIL is released around the native work
+(:64-69); parsed schemas are cached by their source string for the life of the process (:39-54);
+batches cross into pyarrow through the Arrow C Data Interface, zero-copy (:70,88).
+
+Deliberate divergences (documented in DESIGN.md): decode runs on the GPU with NO CPU fallback —
+schemas outside the direct-decode subset raise instead of dropping to the Value-tree path, and a
+missing CUDA device / native library is an error, never a silent Python path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import List
+
+import pyarrow as pa
+
+from . import _build
+
+__all__ = [
+    "deserialize_array", "deserialize_array_threaded", "deserialize_array_threaded_spawn",
+    "serialize_record_batch", "serialize_record_batch_spawn", "lib", "Schema", "decode_packed",
+]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class _ArrowSchema(ctypes.Structure):
+    _fields_ = [("format", ctypes.c_char_p), ("name", ctypes.c_char_p), ("metadata", ctypes.c_char_p),
+                ("flags", ctypes.c_int64), ("n_children", ctypes.c_int64), ("children", ctypes.c_void_p),
+                ("dictionary", ctypes.c_void_p), ("release", ctypes.c_void_p), ("private_data", ctypes.c_void_p)]
+
+
+class _ArrowArray(ctypes.Structure):
+    _fields_ = [("length", ctypes.c_int64), ("null_count", ctypes.c_int64), ("offset", ctypes.c_int64),
+                ("n_buffers", ctypes.c_int64), ("n_children", ctypes.c_int64), ("buffers", ctypes.c_void_p),
+                ("children", ctypes.c_void_p), ("dictionary", ctypes.c_void_p), ("release", ctypes.c_void_p),
+                ("private_data", ctypes.c_void_p)]
+
+
+def _load():
+    """Loads the C-ABI library.  Fails loudly: there is no pure-Python or CPU decode path."""
+    path = os.path.join(_HERE, "libruhvro_b200.so")
+    if not os.path.exists(path):
+        _build.build_lib()
+    L = ctypes.CDLL(path)
+    vp, i64, cp = ctypes.c_void_p, ctypes.c_int64, ctypes.c_char_p
+    L.rv_schema_parse.argtypes = [cp, ctypes.c_size_t, ctypes.POINTER(vp)]
+    L.rv_schema_retain.restype = vp
+    L.rv_schema_retain.argtypes = [vp]
+    L.rv_schema_release.argtypes = [vp]
+    L.rv_schema_release.restype = None
+    L.rv_schema_is_supported.argtypes = [vp]
+    L.rv_schema_export_arrow.argtypes = [vp, vp]
+    L.rv_decode_host.argtypes = [vp, vp, vp, i64, i64, ctypes.POINTER(vp)]
+    L.rv_decode_device.argtypes = [vp, vp, vp, i64, i64, vp, ctypes.POINTER(vp)]
+    L.rv_result_to_host.argtypes = [vp]
+    L.rv_result_num_batches.restype = i64
+    L.rv_result_num_batches.argtypes = [vp]
+    L.rv_result_num_rows.restype = i64
+    L.rv_result_num_rows.argtypes = [vp, i64]
+    L.rv_result_arrow_bytes.restype = i64
+    L.rv_result_arrow_bytes.argtypes = [vp]
+    L.rv_result_export.argtypes = [vp, i64, vp, vp]
+    L.rv_result_export_device.argtypes = [vp, i64, vp, vp]
+    L.rv_result_free.argtypes = [vp]
+    L.rv_result_free.restype = None
+    L.rv_host_alloc.restype = vp
+    L.rv_host_alloc.argtypes = [ctypes.c_size_t]
+    L.rv_host_free.argtypes = [vp]
+    L.rv_host_free.restype = None
+    L.rv_last_timings.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_int]
+    L.rv_last_launch_count.restype = ctypes.c_int
+    L.rv_last_error.restype = cp
+    L.rv_version.restype = cp
+    return L
+
+
+lib = _load()
+
+
+def _last_error() -> str:
+    return (lib.rv_last_error() or b"").decode("utf-8", "replace")
+
+
+def _check(status: int):
+    if status != 0:
+        raise ValueError(_last_error())  # to_py_err (src/lib.rs:25-27)
+
+
+class Schema:
+    """A parsed Avro schema + decode plan (the Arc<Schema> the reference shares across tasks)."""
+
+    def __init__(self, schema_json: str):
+        raw = schema_json.encode("utf-8")
+        h = ctypes.c_void_p()
+        _check(lib.rv_schema_parse(raw, len(raw), ctypes.byref(h)))
+        self.handle = h.value
+        self._arrow = None
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            lib.rv_schema_release(h)
+
+    @property
+    def is_supported(self) -> bool:
+        return bool(lib.rv_schema_is_supported(self.handle))
+
+    @property
+    def arrow_schema(self) -> pa.Schema:
+        if self._arrow is None:
+            cs = _ArrowSchema()
+            _check(lib.rv_schema_export_arrow(self.handle, ctypes.addressof(cs)))
+            self._arrow = pa.Schema._import_from_c(ctypes.addressof(cs))
+        return self._arrow
+
+
+# schema_cache / get_or_parse_schema (src/lib.rs:39-54): unbounded, keyed by the exact string
+_schema_cache = {}
+_schema_lock = threading.Lock()
+
+
+def _get_or_parse_schema(schema: str) -> Schema:
+    if not isinstance(schema, str):
+        raise TypeError("argument 'schema': expected str")
+    with _schema_lock:
+        s = _schema_cache.get(schema)
+    if s is not None:
+        return s
+    parsed = Schema(schema)
+    with _schema_lock:
+        return _schema_cache.setdefault(schema, parsed)
+
+
+def _export_batches(result_handle: int, schema: Schema) -> List[pa.RecordBatch]:
+    """rv_result -> pyarrow batches through the Arrow C Data Interface; frees the result handle
+    (the exported arrays keep the underlying memory alive)."""
+    try:
+        arrow_schema = schema.arrow_schema
+        out = []
+        for i in range(lib.rv_result_num_batches(result_handle)):
+            arr = _ArrowArray()
+            _check(lib.rv_result_export(result_handle, i, ctypes.addressof(arr), None))
+            out.append(pa.RecordBatch._import_from_c(ctypes.addressof(arr), arrow_schema))
+        return out
+    finally:
+        lib.rv_result_free(result_handle)
+
+
+def _ext():
+    import importlib
+    return importlib.import_module(__name__ + "._native")  # built by _build.build_ext(); ImportError is the loud failure
+
+
+def _decode_list(records, schema: str, num_chunks: int) -> List[pa.RecordBatch]:
+    if not isinstance(records, list):
+        raise TypeError("argument 'list': expected a list of bytes")
+    s = _get_or_parse_schema(schema)
+    handle = _ext().decode_list(s.handle, records, int(num_chunks))
+    return _export_batches(handle, s)
+
+
+def deserialize_array(list, schema):  # noqa: A002 - the reference names the parameter `list`
+    """list[bytes] of schemaless Avro datums -> one RecordBatch (src/lib.rs:56-71)."""
+    return _decode_list(list, schema, 1)[0]
+
+
+def deserialize_array_threaded(list, schema, num_chunks):  # noqa: A002
+    """list[bytes] -> `num_chunks` RecordBatches over contiguous row ranges (src/lib.rs:73-89;
+    chunking per ruhvro/src/deserialize.rs:53-68)."""
+    if num_chunks < 0:
+        raise OverflowError("can't convert negative int to unsigned")  # usize extraction in PyO3
+    return _decode_list(list, schema, num_chunks)
+
+
+def deserialize_array_threaded_spawn(list, schema, num_chunks):  # noqa: A002
+    """Same results as deserialize_array_threaded (the reference only changes the tokio primitive,
+    ruhvro/src/deserialize.rs:123-170)."""
+    return deserialize_array_threaded(list, schema, num_chunks)
+
+
+def decode_packed(data, offsets, n: int, schema: str, num_chunks: int = 1) -> List[pa.RecordBatch]:
+    """Packed host buffers (numpy uint8 data + int64 offsets[n+1]) -> batches, through rv_decode_host.
+    This is the C-ABI call a Rust/FFI caller makes; no Python list walk involved."""
+    import numpy as np
+    s = _get_or_parse_schema(schema)
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    h = ctypes.c_void_p()
+    _check(lib.rv_decode_host(s.handle, data.ctypes.data if data.size else None, offsets.ctypes.data, n, num_chunks, ctypes.byref(h)))
+    return _export_batches(h.value, s)
+
+
+def serialize_record_batch(data, schema, num_chunks):
+    """Arrow -> Avro (src/lib.rs:91-106).  The GPU encode path is SURVEY.md 8(f) rank 1 ("next");
+    it is not built yet and, by design, there is no CPU stand-in."""
+    raise NotImplementedError("serialize_record_batch: the GPU Arrow->Avro encoder is not built yet (SURVEY.md 8(f))")
+
+
+def serialize_record_batch_spawn(data, schema, num_chunks):
+    return serialize_record_batch(data, schema, num_chunks)

@@ -1,0 +1,644 @@
+// Host orchestration + C ABI of the decoder (include/ruhvro_b200.h).
+//
+// Replaces the L3 layer of the reference for the direct-decode path:
+//   ruhvro/src/deserialize.rs:25-30,53-121 (dispatch, clamp_chunks, build_slices, fan-out)
+// with: plan upload -> count kernel -> per-chunk scan -> exact-size Arrow arena -> emit kernel ->
+// null counts -> Arrow C Data Interface export.  One CUDA stream per call; device memory comes
+// from the stream-ordered pool, host output memory from a pinned-slab cache.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ruhvro_b200.h"
+#include "arrow_c.h"
+#include "kernels.cuh"
+#include "plan.hpp"
+#include "result.hpp"
+#include "schema.hpp"
+
+using namespace rv;
+
+// ------------------------------------------------------------------------------------------
+// thread-local diagnostics
+// ------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string t_error;
+thread_local float t_timings[6] = {0, 0, 0, 0, 0, 0};
+thread_local int t_launches = 0;
+
+rv_status fail(rv_status st, const std::string& msg) {
+    t_error = msg;
+    return st;
+}
+
+#define RV_CUDA(expr)                                                                                  \
+    do {                                                                                               \
+        cudaError_t e_ = (expr);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(RV_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));              \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// pinned host slabs (cached: cudaHostAlloc of GiB-sized blocks costs hundreds of ms)
+// ------------------------------------------------------------------------------------------
+class PinnedCache {
+  public:
+    void* get(size_t bytes, size_t* actual) {
+        size_t want = round(bytes);
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            auto it = free_.lower_bound(want);
+            if (it != free_.end() && it->first <= want + want / 4 + (1u << 20)) {
+                void* p = it->second;
+                *actual = it->first;
+                cached_ -= it->first;
+                free_.erase(it);
+                return p;
+            }
+        }
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
+            trim(0);
+            if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+        }
+        *actual = want;
+        return p;
+    }
+    void put(void* p, size_t actual) {
+        if (!p) return;
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            if (cached_ + actual <= kMaxCached) {
+                free_.emplace(actual, p);
+                cached_ += actual;
+                return;
+            }
+        }
+        cudaFreeHost(p);
+    }
+    void trim(size_t keep) {
+        std::lock_guard<std::mutex> g(mu_);
+        while (cached_ > keep && !free_.empty()) {
+            auto it = std::prev(free_.end());
+            cudaFreeHost(it->second);
+            cached_ -= it->first;
+            free_.erase(it);
+        }
+    }
+
+  private:
+    static constexpr size_t kMaxCached = size_t(24) << 30;
+    static size_t round(size_t b) {
+        size_t g = b >= (size_t(64) << 20) ? (size_t(16) << 20) : (b >= (1u << 20) ? (1u << 20) : 65536);
+        return ((b ? b : 1) + g - 1) / g * g;
+    }
+    std::mutex mu_;
+    std::multimap<size_t, void*> free_;
+    size_t cached_ = 0;
+};
+
+std::mutex g_host_mu;
+std::map<void*, size_t> g_host_sizes;  // rv_host_alloc blocks -> slab size
+
+PinnedCache& pinned() {
+    static PinnedCache* c = new PinnedCache();  // intentionally leaked: outlives static destructors
+    return *c;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-process CUDA init
+// ------------------------------------------------------------------------------------------
+rv_status ensure_cuda(int* device) {
+    static std::mutex mu;
+    static std::vector<char> inited;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(RV_ERR_CUDA, std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e));
+    RV_CUDA(cudaGetDevice(device));
+    std::lock_guard<std::mutex> g(mu);
+    if (inited.size() < size_t(n)) inited.resize(size_t(n), 0);
+    if (!inited[size_t(*device)]) {
+        RV_CUDA(prepare_kernels());
+        cudaMemPool_t pool;
+        RV_CUDA(cudaDeviceGetDefaultMemPool(&pool, *device));
+        unsigned long long thr = ~0ull;  // keep freed blocks in the pool: allocation becomes a free-list pop
+        RV_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        inited[size_t(*device)] = 1;
+    }
+    return RV_OK;
+}
+
+struct DevBuf {  // stream-ordered device allocation, freed on scope exit unless released
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    cudaError_t alloc(size_t bytes, cudaStream_t st) {
+        s = st;
+        return cudaMallocAsync(&p, bytes ? bytes : 1, st);
+    }
+    ~DevBuf() { if (p) cudaFreeAsync(p, s); }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// schema handle
+// ------------------------------------------------------------------------------------------
+struct DevicePlan {
+    DNode* nodes = nullptr;
+    int32_t* sym_off = nullptr;
+    uint8_t* sym_bytes = nullptr;
+};
+
+struct rv_schema {
+    std::atomic<int> refs{1};
+    std::unique_ptr<AvroNode> avro;
+    bool supported = false;
+    std::string why;              // why it is unsupported / why no plan
+    std::vector<ArrowField> fields;
+    bool has_fields = false;
+    Plan plan;
+    bool has_plan = false;
+    std::mutex mu;
+    std::map<int, DevicePlan> dev;  // device id -> uploaded plan
+};
+
+namespace {
+
+rv_status device_plan(rv_schema* s, int device, DevicePlan* out) {
+    std::lock_guard<std::mutex> g(s->mu);
+    auto it = s->dev.find(device);
+    if (it != s->dev.end()) { *out = it->second; return RV_OK; }
+    DevicePlan d;
+    const Plan& p = s->plan;
+    RV_CUDA(cudaMalloc(&d.nodes, std::max<size_t>(1, p.nodes.size()) * sizeof(DNode)));
+    RV_CUDA(cudaMalloc(&d.sym_off, std::max<size_t>(1, p.sym_off.size()) * 4));
+    RV_CUDA(cudaMalloc(&d.sym_bytes, std::max<size_t>(1, p.sym_bytes.size())));
+    RV_CUDA(cudaMemcpy(d.nodes, p.nodes.data(), p.nodes.size() * sizeof(DNode), cudaMemcpyHostToDevice));
+    if (!p.sym_off.empty()) RV_CUDA(cudaMemcpy(d.sym_off, p.sym_off.data(), p.sym_off.size() * 4, cudaMemcpyHostToDevice));
+    if (!p.sym_bytes.empty()) RV_CUDA(cudaMemcpy(d.sym_bytes, p.sym_bytes.data(), p.sym_bytes.size(), cudaMemcpyHostToDevice));
+    s->dev[device] = d;
+    *out = d;
+    return RV_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// result
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct Arena {  // one decode call's output memory; shared by the result and every exported batch
+    void* dev = nullptr;
+    size_t bytes = 0;
+    void* host = nullptr;
+    size_t host_actual = 0;
+    int device = 0;
+    ~Arena() {
+        if (dev) {
+            int cur = 0;
+            cudaGetDevice(&cur);
+            if (cur != device) cudaSetDevice(device);
+            cudaFreeAsync(dev, nullptr);
+            if (cur != device) cudaSetDevice(cur);
+        }
+        if (host) pinned().put(host, host_actual);
+    }
+};
+
+}  // namespace
+
+struct rv_result {
+    rv_schema* schema = nullptr;
+    std::shared_ptr<Arena> arena;
+    std::vector<ChunkOut> chunks;
+    bool on_host = false;
+    int64_t arrow_bytes = 0;
+    ~rv_result() { if (schema) rv_schema_release(schema); }
+};
+
+namespace {
+
+const char* err_text(uint32_t code) {
+    switch (code) {
+        case E_EOF: return "unexpected end of buffer";
+        case E_VARINT: return "zigzag varint too long";
+        case E_BOOL: return "invalid boolean byte";
+        case E_NEG_LEN: return "negative string length";
+        case E_BRANCH: return "invalid union branch index";
+        case E_ENUM: return "enum index out of range";
+        case E_OVERFLOW: return "Arrow i32 offset overflow (or malformed input offsets)";
+        default: return "decode error";
+    }
+}
+
+// ---- the decode call ------------------------------------------------------------------------
+rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d_offsets, int64_t n, int64_t num_chunks,
+                           int64_t total_bytes_hint, cudaStream_t stream, int device, rv_result** out) {
+    const Plan& plan = s->plan;
+    const int S = int(plan.streams.size());
+    const int n_slots = int(plan.slots.size());
+    // clamp_chunks (deserialize.rs:53-55)
+    int64_t k64 = clamp_chunks(num_chunks, n);
+    if (k64 > (int64_t(1) << 24)) return fail(RV_ERR_INVALID, "num_chunks above 2^24 is not supported");
+    const int k = int(k64);
+    const int64_t chunk_rows = n / k;  // build_slices (:57-68)
+    const int64_t last_rows = n - chunk_rows * (k - 1);
+
+    auto res = std::make_unique<rv_result>();
+    res->schema = rv_schema_retain(s);
+    res->arena = std::make_shared<Arena>();
+    res->arena->device = device;
+
+    for (int i = 0; i < 6; ++i) t_timings[i] = 0;
+    t_launches = 0;
+
+    std::vector<unsigned long long> chunk_tot(size_t(k) * size_t(std::max(S, 1)), 0ull);
+    DecodeParams p{};
+    DevBuf tile_agg, tile_base, d_chunk_tot, d_err, d_bufs;
+    cudaEvent_t ev[8];
+    for (auto& e : ev) RV_CUDA(cudaEventCreate(&e));
+    struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 8; ++i) cudaEventDestroy(e[i]); } } evg{ev};
+    size_t smem = 0;
+
+    if (n > 0) {
+        DevicePlan dp;
+        rv_status st = device_plan(s, device, &dp);
+        if (st) return st;
+        const int64_t tpc = std::max<int64_t>(1, (chunk_rows + kBlock - 1) / kBlock);
+        const int64_t tiles_last = (last_rows + kBlock - 1) / kBlock;
+        const int64_t n_tiles = tpc * (k - 1) + tiles_last;
+        if (n_tiles > 0x7FFFFFF0ll) return fail(RV_ERR_INVALID, "too many records for one call");
+
+        int64_t total_bytes = total_bytes_hint;
+        if (total_bytes < 0) {
+            int64_t ends[2];
+            RV_CUDA(cudaMemcpyAsync(&ends[0], d_offsets, 8, cudaMemcpyDeviceToHost, stream));
+            RV_CUDA(cudaMemcpyAsync(&ends[1], d_offsets + n, 8, cudaMemcpyDeviceToHost, stream));
+            RV_CUDA(cudaStreamSynchronize(stream));
+            total_bytes = ends[1] - ends[0];
+        }
+        // shared-memory budget: plan + cursors are fixed; the rest stages the tile's bytes
+        const size_t fixed = decode_smem_bytes(int(plan.nodes.size()), S, 0);
+        const size_t limit = 227 * 1024;
+        if (fixed + 1024 > limit) return fail(RV_ERR_SCHEMA, "schema too wide for the shared-memory cursor table");
+        const double avg = total_bytes > 0 ? double(total_bytes) / double(n) : 16.0;
+        size_t want = size_t(avg * kBlock * 1.25) + 1024;
+        want = (want + 1023) & ~size_t(1023);
+        want = std::max<size_t>(want, 8192);
+        const size_t room = (limit - fixed) & ~size_t(15);
+        // prefer >= 2 CTAs per SM when the tile fits in half the shared memory
+        const size_t half = (limit / 2 > fixed + 4096) ? ((limit / 2 - fixed) & ~size_t(15)) : 0;
+        size_t cap = want <= half ? want : std::min(want, room);
+        smem = fixed + cap;
+
+        p.data = d_data; p.offsets = d_offsets; p.n = n; p.chunk_rows = chunk_rows; p.k = k;
+        p.tiles_per_chunk = int32_t(tpc); p.n_tiles = int32_t(n_tiles);
+        p.nodes = dp.nodes; p.n_nodes = int32_t(plan.nodes.size()); p.n_streams = S; p.n_slots = n_slots;
+        p.sym_off = dp.sym_off; p.sym_bytes = dp.sym_bytes;
+        p.smem_data_cap = uint32_t(cap);
+        RV_CUDA(tile_agg.alloc(size_t(std::max(S, 1)) * size_t(n_tiles) * 4, stream));
+        RV_CUDA(tile_base.alloc(size_t(std::max(S, 1)) * size_t(n_tiles) * 4, stream));
+        RV_CUDA(d_chunk_tot.alloc(chunk_tot.size() * 8, stream));
+        RV_CUDA(d_err.alloc(8, stream));
+        p.tile_agg = static_cast<uint32_t*>(tile_agg.p);
+        p.tile_base = static_cast<uint32_t*>(tile_base.p);
+        p.chunk_tot = static_cast<unsigned long long*>(d_chunk_tot.p);
+        p.err = static_cast<unsigned long long*>(d_err.p);
+        p.bufs = nullptr;
+        RV_CUDA(cudaMemsetAsync(d_err.p, 0xFF, 8, stream));
+
+        RV_CUDA(cudaEventRecord(ev[0], stream));
+        launch_count(p, smem, stream);
+        RV_CUDA(cudaEventRecord(ev[1], stream));
+        launch_scan(p, stream);
+        RV_CUDA(cudaEventRecord(ev[2], stream));
+        RV_CUDA(cudaGetLastError());
+        t_launches += S > 0 ? 2 : 1;
+
+        unsigned long long err_word = ~0ull;
+        RV_CUDA(cudaMemcpyAsync(&err_word, d_err.p, 8, cudaMemcpyDeviceToHost, stream));
+        if (S > 0) RV_CUDA(cudaMemcpyAsync(chunk_tot.data(), d_chunk_tot.p, chunk_tot.size() * 8, cudaMemcpyDeviceToHost, stream));
+        RV_CUDA(cudaStreamSynchronize(stream));
+        if (err_word != ~0ull) {
+            const uint32_t code = uint32_t(err_word & 0xFF);
+            return fail(rv_status(code), std::string(err_text(code)) + " (record " + std::to_string(err_word >> 8) + ")");
+        }
+    }
+
+    // ---- exact arena layout -------------------------------------------------------------
+    Layout L = compute_layout(plan, n, k, chunk_tot.data());
+    res->chunks = std::move(L.chunks);
+    const size_t zero_bytes = L.zero_bytes, total = L.total_bytes;
+    res->arena->bytes = total;
+    RV_CUDA(cudaMallocAsync(&res->arena->dev, std::max<size_t>(total, 64), stream));
+    uint8_t* arena = static_cast<uint8_t*>(res->arena->dev);
+
+    if (n > 0) {
+        if (zero_bytes) RV_CUDA(cudaMemsetAsync(arena, 0, zero_bytes, stream));
+        // pointer table
+        std::vector<void*> h_bufs(size_t(k) * size_t(n_slots));
+        for (int j = 0; j < k; ++j)
+            for (int sl = 0; sl < n_slots; ++sl) h_bufs[size_t(j) * size_t(n_slots) + size_t(sl)] = arena + res->chunks[size_t(j)].slot_off[size_t(sl)];
+        RV_CUDA(d_bufs.alloc(h_bufs.size() * sizeof(void*), stream));
+        RV_CUDA(cudaMemcpyAsync(d_bufs.p, h_bufs.data(), h_bufs.size() * sizeof(void*), cudaMemcpyHostToDevice, stream));
+        p.bufs = static_cast<void* const*>(d_bufs.p);
+
+        RV_CUDA(cudaEventRecord(ev[3], stream));
+        launch_emit(p, smem, stream);
+        RV_CUDA(cudaEventRecord(ev[4], stream));
+        RV_CUDA(cudaGetLastError());
+        t_launches += 1;
+
+        // null counts of every validity bitmap
+        const int nv = int(plan.validity_slots.size());
+        std::vector<long long> ones(size_t(k) * size_t(std::max(nv, 1)), 0);
+        DevBuf d_jobs, d_ones;
+        if (nv > 0) {
+            std::vector<NullCountJob> jobs(size_t(k) * size_t(nv));
+            for (int j = 0; j < k; ++j)
+                for (int v = 0; v < nv; ++v) {
+                    const int sl = plan.validity_slots[size_t(v)];
+                    const ChunkOut& c = res->chunks[size_t(j)];
+                    jobs[size_t(j) * size_t(nv) + size_t(v)] =
+                        NullCountJob{reinterpret_cast<const uint32_t*>(arena + c.slot_off[size_t(sl)]), c.space_rows[size_t(plan.slots[size_t(sl)].space)]};
+                }
+            RV_CUDA(d_jobs.alloc(jobs.size() * sizeof(NullCountJob), stream));
+            RV_CUDA(d_ones.alloc(ones.size() * 8, stream));
+            RV_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(NullCountJob), cudaMemcpyHostToDevice, stream));
+            RV_CUDA(cudaMemsetAsync(d_ones.p, 0, ones.size() * 8, stream));
+            launch_null_count(static_cast<const NullCountJob*>(d_jobs.p), int(jobs.size()), static_cast<long long*>(d_ones.p), stream);
+            RV_CUDA(cudaGetLastError());
+            t_launches += 1;
+            RV_CUDA(cudaEventRecord(ev[5], stream));
+            RV_CUDA(cudaMemcpyAsync(ones.data(), d_ones.p, ones.size() * 8, cudaMemcpyDeviceToHost, stream));
+        } else {
+            RV_CUDA(cudaEventRecord(ev[5], stream));
+        }
+        RV_CUDA(cudaStreamSynchronize(stream));
+        for (int j = 0; j < k; ++j)
+            for (int v = 0; v < nv; ++v) {
+                const int sl = plan.validity_slots[size_t(v)];
+                ChunkOut& c = res->chunks[size_t(j)];
+                c.null_count[size_t(sl)] = c.space_rows[size_t(plan.slots[size_t(sl)].space)] - ones[size_t(j) * size_t(nv) + size_t(v)];
+            }
+        cudaEventElapsedTime(&t_timings[0], ev[0], ev[1]);
+        cudaEventElapsedTime(&t_timings[1], ev[1], ev[2]);
+        cudaEventElapsedTime(&t_timings[2], ev[3], ev[4]);
+        cudaEventElapsedTime(&t_timings[3], ev[4], ev[5]);
+    } else {
+        // n == 0: one empty batch; offsets buffers hold the single 0 entry
+        RV_CUDA(cudaMemsetAsync(arena, 0, std::max<size_t>(total, 64), stream));
+        RV_CUDA(cudaStreamSynchronize(stream));
+    }
+    res->arrow_bytes = exported_bytes(plan, res->chunks);
+    *out = res.release();
+    return RV_OK;
+}
+
+rv_status check_decodable(const rv_schema* s) {
+    if (!s) return fail(RV_ERR_INVALID, "null schema handle");
+    if (!s->supported)
+        return fail(RV_ERR_SCHEMA, "schema is outside the direct-decode subset (" + s->why + "); this library has no Value-tree CPU fallback");
+    if (!s->has_plan) return fail(RV_ERR_SCHEMA, s->why);
+    return RV_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+rv_status rv_schema_parse(const char* json, size_t len, rv_schema** out) {
+    if (!json || !out) return fail(RV_ERR_INVALID, "null argument");
+    *out = nullptr;
+    try {
+        auto s = std::make_unique<rv_schema>();
+        s->avro = parse_avro_schema(json, len);
+        s->supported = is_supported(*s->avro, &s->why);
+        if (s->avro->k == AK::Record) {
+            try {
+                s->fields = to_arrow_fields(*s->avro);
+                s->has_fields = true;
+            } catch (const std::exception& e) {
+                if (s->supported) { s->supported = false; s->why = e.what(); }
+            }
+        }
+        if (s->supported && s->has_fields) {
+            try {
+                s->plan = build_plan(*s->avro, s->fields);
+                s->has_plan = true;
+            } catch (const std::exception& e) {
+                s->why = e.what();
+            }
+        }
+        *out = s.release();
+        return RV_OK;
+    } catch (const std::exception& e) {
+        return fail(RV_ERR_SCHEMA, e.what());
+    }
+}
+
+rv_schema* rv_schema_retain(rv_schema* s) {
+    if (s) s->refs.fetch_add(1, std::memory_order_relaxed);
+    return s;
+}
+
+void rv_schema_release(rv_schema* s) {
+    if (!s) return;
+    if (s->refs.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        for (auto& kv : s->dev) {
+            cudaFree(kv.second.nodes);
+            cudaFree(kv.second.sym_off);
+            cudaFree(kv.second.sym_bytes);
+        }
+        delete s;
+    }
+}
+
+int rv_schema_is_supported(const rv_schema* s) { return s && s->supported && s->has_plan ? 1 : 0; }
+
+rv_status rv_schema_export_arrow(const rv_schema* s, struct ArrowSchema* out) {
+    if (!s || !out) return fail(RV_ERR_INVALID, "null argument");
+    if (!s->has_fields) return fail(RV_ERR_SCHEMA, s->why.empty() ? "top-level schema is not a record" : s->why);
+    try {
+        export_arrow_schema(s->fields, out);
+        return RV_OK;
+    } catch (const std::exception& e) {
+        return fail(RV_ERR_SCHEMA, e.what());
+    }
+}
+
+rv_status rv_decode_device(const rv_schema* s, const uint8_t* d_data, const int64_t* d_offsets, int64_t n,
+                           int64_t num_chunks, void* cuda_stream, rv_result** out) {
+    if (!out) return fail(RV_ERR_INVALID, "null argument");
+    *out = nullptr;
+    rv_status st = check_decodable(s);
+    if (st) return st;
+    if (n < 0 || (n > 0 && (!d_data || !d_offsets))) return fail(RV_ERR_INVALID, "bad input pointers");
+    if (reinterpret_cast<uintptr_t>(d_data) & 15u) return fail(RV_ERR_INVALID, "d_data must be 16-byte aligned");
+    int device = 0;
+    st = ensure_cuda(&device);
+    if (st) return st;
+    try {
+        return decode_on_device(const_cast<rv_schema*>(s), d_data, d_offsets, n, num_chunks, -1, static_cast<cudaStream_t>(cuda_stream), device, out);
+    } catch (const std::exception& e) {
+        return fail(RV_ERR_INVALID, e.what());
+    }
+}
+
+rv_status rv_result_to_host(rv_result* r) {
+    if (!r) return fail(RV_ERR_INVALID, "null result");
+    if (r->on_host) return RV_OK;
+    Arena& a = *r->arena;
+    size_t actual = 0;
+    void* h = pinned().get(std::max<size_t>(a.bytes, 64), &actual);
+    if (!h) return fail(RV_ERR_CUDA, "pinned host allocation failed");
+    a.host = h;
+    a.host_actual = actual;
+    cudaEvent_t e0, e1;
+    RV_CUDA(cudaEventCreate(&e0));
+    RV_CUDA(cudaEventCreate(&e1));
+    cudaEventRecord(e0, nullptr);
+    cudaError_t e = cudaMemcpyAsync(h, a.dev, a.bytes, cudaMemcpyDeviceToHost, nullptr);
+    cudaEventRecord(e1, nullptr);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+    cudaEventElapsedTime(&t_timings[5], e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (e != cudaSuccess) return fail(RV_ERR_CUDA, std::string("device->host copy: ") + cudaGetErrorString(e));
+    r->on_host = true;
+    return RV_OK;
+}
+
+rv_status rv_decode_host(const rv_schema* s, const uint8_t* data, const int64_t* offsets, int64_t n,
+                         int64_t num_chunks, rv_result** out) {
+    if (!out) return fail(RV_ERR_INVALID, "null argument");
+    *out = nullptr;
+    rv_status st = check_decodable(s);
+    if (st) return st;
+    if (n < 0 || (n > 0 && (!data || !offsets))) return fail(RV_ERR_INVALID, "bad input pointers");
+    int device = 0;
+    st = ensure_cuda(&device);
+    if (st) return st;
+    cudaStream_t stream = nullptr;
+    DevBuf d_data, d_off;
+    int64_t total = 0;
+    float h2d_ms = 0;
+    if (n > 0) {
+        const int64_t b0 = offsets[0];
+        total = offsets[n] - b0;
+        if (total < 0) return fail(RV_ERR_INVALID, "offsets are not monotonic");
+        RV_CUDA(d_data.alloc(size_t(total) + 64, stream));
+        RV_CUDA(d_off.alloc(size_t(n + 1) * 8, stream));
+        cudaEvent_t e0, e1;
+        RV_CUDA(cudaEventCreate(&e0));
+        RV_CUDA(cudaEventCreate(&e1));
+        cudaEventRecord(e0, stream);
+        // The device copy keeps the caller's absolute offsets: d_data is biased so that
+        // d_data + offsets[i] addresses record i (offsets[0] need not be 0).
+        cudaError_t e = cudaMemcpyAsync(static_cast<uint8_t*>(d_data.p) + (b0 & 15), data + b0, size_t(total), cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_off.p, offsets, size_t(n + 1) * 8, cudaMemcpyHostToDevice, stream);
+        cudaEventRecord(e1, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        cudaEventElapsedTime(&h2d_ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        if (e != cudaSuccess) return fail(RV_ERR_CUDA, std::string("host->device copy: ") + cudaGetErrorString(e));
+    }
+    try {
+        // bias: kernel address of byte x is base + x, so base = copy_start - b0 (kept 16-byte aligned by the b0&15 shift)
+        const uint8_t* base = n > 0 ? static_cast<const uint8_t*>(d_data.p) + (offsets[0] & 15) - offsets[0] : nullptr;
+        st = decode_on_device(const_cast<rv_schema*>(s), base, static_cast<const int64_t*>(d_off.p), n, num_chunks, total, stream, device, out);
+    } catch (const std::exception& e) {
+        return fail(RV_ERR_INVALID, e.what());
+    }
+    if (st) return st;
+    t_timings[4] = h2d_ms;
+    st = rv_result_to_host(*out);
+    if (st) { rv_result_free(*out); *out = nullptr; }
+    return st;
+}
+
+int64_t rv_result_num_batches(const rv_result* r) { return r ? int64_t(r->chunks.size()) : 0; }
+int64_t rv_result_num_rows(const rv_result* r, int64_t batch) {
+    if (!r || batch < 0 || batch >= int64_t(r->chunks.size())) return -1;
+    return r->chunks[size_t(batch)].rows;
+}
+int64_t rv_result_arrow_bytes(const rv_result* r) { return r ? r->arrow_bytes : 0; }
+
+rv_status rv_result_export(rv_result* r, int64_t batch, struct ArrowArray* out_array, struct ArrowSchema* out_schema) {
+    if (!r || !out_array) return fail(RV_ERR_INVALID, "null argument");
+    if (batch < 0 || batch >= int64_t(r->chunks.size())) return fail(RV_ERR_INVALID, "batch index out of range");
+    if (!r->on_host) return fail(RV_ERR_INVALID, "result is device-resident: call rv_result_to_host() or rv_result_export_device()");
+    if (out_schema) {
+        rv_status st = rv_schema_export_arrow(r->schema, out_schema);
+        if (st) return st;
+    }
+    export_batch(r->schema->plan, r->chunks[size_t(batch)], static_cast<const uint8_t*>(r->arena->host), r->arena, out_array);
+    return RV_OK;
+}
+
+rv_status rv_result_export_device(rv_result* r, int64_t batch, struct ArrowDeviceArray* out_array, struct ArrowSchema* out_schema) {
+    if (!r || !out_array) return fail(RV_ERR_INVALID, "null argument");
+    if (batch < 0 || batch >= int64_t(r->chunks.size())) return fail(RV_ERR_INVALID, "batch index out of range");
+    if (out_schema) {
+        rv_status st = rv_schema_export_arrow(r->schema, out_schema);
+        if (st) return st;
+    }
+    export_batch(r->schema->plan, r->chunks[size_t(batch)], static_cast<const uint8_t*>(r->arena->dev), r->arena, &out_array->array);
+    out_array->device_id = r->arena->device;
+    out_array->device_type = ARROW_DEVICE_CUDA;
+    out_array->sync_event = nullptr;  // the decode call synchronised its stream before returning
+    out_array->reserved[0] = out_array->reserved[1] = out_array->reserved[2] = 0;
+    return RV_OK;
+}
+
+void rv_result_free(rv_result* r) { delete r; }
+
+void* rv_host_alloc(size_t bytes) {
+    size_t actual = 0;
+    void* p = pinned().get(bytes, &actual);
+    if (!p) {
+        t_error = "cudaHostAlloc failed (no CUDA device, or out of pinnable memory)";
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> g(g_host_mu);
+    g_host_sizes[p] = actual;
+    return p;
+}
+void rv_host_free(void* p) {
+    if (!p) return;
+    size_t actual = 0;
+    {
+        std::lock_guard<std::mutex> g(g_host_mu);
+        auto it = g_host_sizes.find(p);
+        if (it == g_host_sizes.end()) return;
+        actual = it->second;
+        g_host_sizes.erase(it);
+    }
+    pinned().put(p, actual);  // back to the slab cache: re-pinning GiB-sized blocks costs ~100s of ms
+}
+
+int rv_last_timings(float* out_ms, int cap) {
+    int n = cap < 6 ? cap : 6;
+    for (int i = 0; i < n; ++i) out_ms[i] = t_timings[i];
+    return n;
+}
+int rv_last_launch_count(void) { return t_launches; }
+const char* rv_last_error(void) { return t_error.c_str(); }
+const char* rv_version(void) { return "pyruhvro_b200 0.1.0 (sm_100a)"; }
+
+}  // extern "C"

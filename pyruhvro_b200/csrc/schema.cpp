@@ -1,0 +1,405 @@
+// See schema.hpp for the reference lines each function mirrors.
+#include "schema.hpp"
+
+#include <cstdlib>
+#include <cstring>
+#include <set>
+#include <stdexcept>
+
+#include "json.hpp"
+
+namespace rv {
+namespace {
+
+[[noreturn]] void bad(const std::string& what) { throw std::runtime_error("invalid Avro schema: " + what); }
+
+std::unique_ptr<AvroNode> mk(AK k) {
+    auto n = std::make_unique<AvroNode>();
+    n->k = k;
+    return n;
+}
+std::unique_ptr<AvroNode> unsupported(const std::string& what) {
+    auto n = mk(AK::Unsupported);
+    n->what = what;
+    return n;
+}
+
+// Name resolution as apache-avro does it: a dotted name carries its own namespace,
+// otherwise the "namespace" attribute, otherwise the enclosing namespace.
+void resolve_name(const Json& j, const std::string& enclosing_ns, std::string* fullname, std::string* ns) {
+    const Json* nm = j.find("name");
+    if (!nm || !nm->is_string() || nm->str.empty()) bad("named type without a \"name\"");
+    const std::string& name = nm->str;
+    size_t dot = name.rfind('.');
+    std::string shortname;
+    if (dot != std::string::npos) {
+        *ns = name.substr(0, dot);
+        shortname = name.substr(dot + 1);
+    } else {
+        const Json* nsj = j.find("namespace");
+        *ns = (nsj && nsj->is_string()) ? nsj->str : enclosing_ns;
+        shortname = name;
+    }
+    *fullname = ns->empty() ? shortname : *ns + "." + shortname;
+}
+
+void read_doc_aliases(const Json& j, const std::string& ns, AvroNode* n) {
+    if (const Json* d = j.find("doc"); d && d->is_string()) { n->has_doc = true; n->doc = d->str; }
+    if (const Json* a = j.find("aliases"); a && a->kind == Json::Array) {
+        n->has_aliases = true;
+        for (auto& al : a->arr) {
+            if (!al.is_string()) bad("alias must be a string");
+            if (al.str.find('.') == std::string::npos && !ns.empty()) n->aliases.push_back(ns + "." + al.str);
+            else n->aliases.push_back(al.str);
+        }
+    }
+}
+
+std::unique_ptr<AvroNode> primitive(const std::string& t, const Json* obj) {
+    std::string lt;
+    if (obj)
+        if (const Json* l = obj->find("logicalType"); l && l->is_string()) lt = l->str;
+    if (t == "null") return mk(AK::Null);
+    if (t == "boolean") return mk(AK::Bool);
+    if (t == "float") return mk(AK::Float);
+    if (t == "double") return mk(AK::Double);
+    if (t == "int") {
+        if (lt == "date") return mk(AK::Date);
+        if (lt == "time-millis") return unsupported("time-millis");
+        return mk(AK::Int);  // unknown logical types degrade to the base type
+    }
+    if (t == "long") {
+        if (lt == "timestamp-millis") return mk(AK::TsMillis);
+        if (lt == "timestamp-micros") return mk(AK::TsMicros);
+        if (lt == "time-micros" || lt == "timestamp-nanos" || lt == "local-timestamp-millis" ||
+            lt == "local-timestamp-micros" || lt == "local-timestamp-nanos")
+            return unsupported(lt);
+        return mk(AK::Long);
+    }
+    if (t == "string") {
+        if (lt == "uuid") return unsupported("uuid");
+        return mk(AK::String);
+    }
+    if (t == "bytes") return unsupported(lt == "decimal" ? "decimal" : "bytes");
+    if (t == "fixed") return unsupported(lt.empty() ? "fixed" : lt);
+    return unsupported("named type reference \"" + t + "\"");  // Schema::Ref (fast_decode.rs:59)
+}
+
+// Key used for the "unions may not contain duplicate types" rule.
+std::string union_key(const AvroNode& n) {
+    switch (n.k) {
+        case AK::Record: case AK::Enum: return "named:" + n.fullname;
+        case AK::Unsupported: return "unsupported:" + n.what;
+        default: return "kind:" + std::to_string(int(n.k));
+    }
+}
+
+std::unique_ptr<AvroNode> parse_node(const Json& j, const std::string& ns, int depth) {
+    if (depth > 64) bad("schema nesting too deep");
+    if (j.kind == Json::String) return primitive(j.str, nullptr);
+    if (j.kind == Json::Array) {
+        auto u = mk(AK::Union);
+        std::set<std::string> seen;
+        for (auto& v : j.arr) {
+            auto c = parse_node(v, ns, depth + 1);
+            if (c->k == AK::Union) bad("unions may not immediately contain other unions");
+            if (!seen.insert(union_key(*c)).second) bad("unions cannot contain duplicate types");
+            u->sub.push_back(std::move(c));
+        }
+        if (u->sub.empty()) bad("empty union");
+        return u;
+    }
+    if (j.kind != Json::Object) bad("a schema must be a string, array or object");
+    const Json* t = j.find("type");
+    if (!t) bad("object schema without \"type\"");
+    if (!t->is_string()) return parse_node(*t, ns, depth + 1);
+    const std::string& ts = t->str;
+    if (ts == "record" || ts == "error") {
+        auto r = mk(AK::Record);
+        std::string rns;
+        resolve_name(j, ns, &r->fullname, &rns);
+        read_doc_aliases(j, rns, r.get());
+        const Json* fs = j.find("fields");
+        if (!fs || fs->kind != Json::Array) bad("record without a \"fields\" array");
+        for (auto& fj : fs->arr) {
+            if (fj.kind != Json::Object) bad("record field must be an object");
+            AvroField f;
+            const Json* fn = fj.find("name");
+            const Json* ft = fj.find("type");
+            if (!fn || !fn->is_string() || !ft) bad("record field needs \"name\" and \"type\"");
+            f.name = fn->str;
+            f.type = parse_node(*ft, rns, depth + 1);
+            if (const Json* d = fj.find("doc"); d && d->is_string()) { f.has_doc = true; f.doc = d->str; }
+            r->fields.push_back(std::move(f));
+        }
+        return r;
+    }
+    if (ts == "enum") {
+        auto e = mk(AK::Enum);
+        std::string ens;
+        resolve_name(j, ns, &e->fullname, &ens);
+        read_doc_aliases(j, ens, e.get());
+        const Json* sy = j.find("symbols");
+        if (!sy || sy->kind != Json::Array) bad("enum without a \"symbols\" array");
+        for (auto& s : sy->arr) {
+            if (!s.is_string()) bad("enum symbols must be strings");
+            e->symbols.push_back(s.str);
+        }
+        return e;
+    }
+    if (ts == "array" || ts == "map") {
+        auto a = mk(ts == "array" ? AK::Array : AK::Map);
+        const Json* it = j.find(ts == "array" ? "items" : "values");
+        if (!it) bad(ts == "array" ? "array without \"items\"" : "map without \"values\"");
+        a->sub.push_back(parse_node(*it, ns, depth + 1));
+        return a;
+    }
+    return primitive(ts, &j);
+}
+
+bool supported_inner(const AvroNode& n, std::string* why) {
+    switch (n.k) {
+        case AK::Int: case AK::Long: case AK::Float: case AK::Double: case AK::Bool: case AK::String: case AK::Null:
+        case AK::Date: case AK::TsMillis: case AK::TsMicros: case AK::Enum:
+            return true;
+        case AK::Record:
+            for (auto& f : n.fields)
+                if (!supported_inner(*f.type, why)) return false;
+            return true;
+        case AK::Union: case AK::Array: case AK::Map:
+            for (auto& s : n.sub)
+                if (!supported_inner(*s, why)) return false;
+            return true;
+        default:
+            if (why) *why = n.what;
+            return false;
+    }
+}
+
+// ---- schema_translate.rs ----------------------------------------------------
+
+const char* default_field_name(AT t) {  // :155-220
+    switch (t) {
+        case AT::Null: return "null";
+        case AT::Bool: return "bit";
+        case AT::Int32: return "int";
+        case AT::Int64: return "bigint";
+        case AT::Float32: return "float4";
+        case AT::Float64: return "float8";
+        case AT::Date32: return "dateday";
+        case AT::TsMs: return "timestampmilli";
+        case AT::TsUs: return "timestampmicro";
+        case AT::Utf8: return "varchar";
+        case AT::List: return "list";
+        case AT::Struct: return "struct";
+        case AT::SparseUnion: return "union";
+        case AT::Map: throw std::runtime_error("a map cannot be an unnamed union variant (reference: default_field_name is unimplemented for Map, schema_translate.rs:212)");
+    }
+    return "";
+}
+
+using Props = std::vector<std::pair<std::string, std::string>>;
+
+// schema_to_field_with_props, :43-153.  `name == nullptr` means None.
+ArrowField to_field(const AvroNode& s, const std::string* name, bool nullable, const Props* props) {
+    ArrowField f;
+    switch (s.k) {
+        case AK::Null: f.type = AT::Null; break;
+        case AK::Bool: f.type = AT::Bool; break;
+        case AK::Int: f.type = AT::Int32; break;
+        case AK::Long: f.type = AT::Int64; break;
+        case AK::Float: f.type = AT::Float32; break;
+        case AK::Double: f.type = AT::Float64; break;
+        case AK::String: f.type = AT::Utf8; break;
+        case AK::Date: f.type = AT::Date32; break;
+        case AK::TsMillis: f.type = AT::TsMs; break;
+        case AK::TsMicros: f.type = AT::TsUs; break;
+        case AK::Array: {  // :60-65
+            f.type = AT::List;
+            std::string item = "item";
+            f.children.push_back(to_field(*s.sub[0], &item, true, nullptr));
+            break;
+        }
+        case AK::Map: {  // :66-75
+            f.type = AT::Map;
+            std::string vname = "values";
+            ArrowField value = to_field(*s.sub[0], &vname, false, nullptr);
+            ArrowField key;
+            key.name = "keys"; key.type = AT::Utf8; key.nullable = false;
+            ArrowField entries;
+            entries.name = "entries"; entries.type = AT::Struct; entries.nullable = nullable;  // sic: the map's own nullability
+            entries.children.push_back(std::move(key));
+            entries.children.push_back(std::move(value));
+            f.children.push_back(std::move(entries));
+            break;
+        }
+        case AK::Union: {  // :76-105
+            bool has_null = false;
+            for (auto& v : s.sub) has_null |= v->k == AK::Null;
+            if (has_null && s.sub.size() == 2) {
+                nullable = true;
+                const AvroNode* inner = nullptr;
+                for (auto& v : s.sub)
+                    if (v->k != AK::Null) { inner = v.get(); break; }
+                if (!inner) throw std::runtime_error("Avro union contains duplicate null variants");
+                ArrowField in = to_field(*inner, nullptr, true, nullptr);
+                f.type = in.type;
+                f.children = std::move(in.children);
+            } else {
+                if (has_null) nullable = true;
+                if (s.sub.size() > 127) throw std::runtime_error("union with more than 127 variants (Arrow type ids are i8)");
+                f.type = AT::SparseUnion;
+                for (auto& v : s.sub) f.children.push_back(to_field(*v, nullptr, true, nullptr));
+            }
+            break;
+        }
+        case AK::Record: {  // :106-123
+            f.type = AT::Struct;
+            for (auto& fld : s.fields) {
+                Props p;
+                if (fld.has_doc) p.emplace_back("avro::doc", fld.doc);
+                f.children.push_back(to_field(*fld.type, &fld.name, nullable, &p));
+            }
+            break;
+        }
+        case AK::Enum: {  // :124-132 — early return: metadata is never attached
+            f.type = AT::Utf8;
+            f.name = (name && !name->empty()) ? *name : s.fullname;
+            f.nullable = nullable;
+            return f;
+        }
+        case AK::Unsupported:
+            throw std::runtime_error("schema construct outside the direct-decode subset: " + s.what);
+    }
+    f.name = name ? *name : std::string(default_field_name(f.type));
+    f.nullable = nullable;
+    if (props) f.metadata = *props;
+    return f;
+}
+
+Props external_props(const AvroNode& s) {  // :222-266
+    Props p;
+    if (s.k == AK::Record || s.k == AK::Enum) {
+        if (s.has_doc) p.emplace_back("avro::doc", s.doc);
+        if (s.has_aliases) {
+            std::string joined = "[";
+            for (size_t i = 0; i < s.aliases.size(); ++i) {
+                if (i) joined += ",";
+                joined += s.aliases[i];
+            }
+            joined += "]";
+            p.emplace_back("avro::aliases", joined);
+        }
+    }
+    return p;
+}
+
+// ---- Arrow C schema export ----------------------------------------------------
+
+struct SchemaPrivate {
+    std::string format, name, metadata;
+    std::vector<ArrowSchema> child_storage;
+    std::vector<ArrowSchema*> child_ptrs;
+};
+
+void release_schema(ArrowSchema* s) {
+    if (!s || !s->release) return;
+    for (int64_t i = 0; i < s->n_children; ++i)
+        if (s->children[i] && s->children[i]->release) s->children[i]->release(s->children[i]);
+    delete static_cast<SchemaPrivate*>(s->private_data);
+    s->release = nullptr;
+}
+
+std::string format_of(const ArrowField& f) {
+    switch (f.type) {
+        case AT::Null: return "n";
+        case AT::Bool: return "b";
+        case AT::Int32: return "i";
+        case AT::Int64: return "l";
+        case AT::Float32: return "f";
+        case AT::Float64: return "g";
+        case AT::Utf8: return "u";
+        case AT::Date32: return "tdD";
+        case AT::TsMs: return "tsm:";
+        case AT::TsUs: return "tsu:";
+        case AT::Struct: return "+s";
+        case AT::List: return "+l";
+        case AT::Map: return "+m";
+        case AT::SparseUnion: {
+            std::string s = "+us:";
+            for (size_t i = 0; i < f.children.size(); ++i) {
+                if (i) s += ",";
+                s += std::to_string(i);
+            }
+            return s;
+        }
+    }
+    return "n";
+}
+
+void put_i32(std::string& o, int32_t v) { o.append(reinterpret_cast<const char*>(&v), 4); }
+
+void fill_schema(const ArrowField& f, ArrowSchema* out) {
+    auto* p = new SchemaPrivate();
+    p->format = format_of(f);
+    p->name = f.name;
+    if (!f.metadata.empty()) {
+        put_i32(p->metadata, int32_t(f.metadata.size()));
+        for (auto& kv : f.metadata) {
+            put_i32(p->metadata, int32_t(kv.first.size())); p->metadata += kv.first;
+            put_i32(p->metadata, int32_t(kv.second.size())); p->metadata += kv.second;
+        }
+    }
+    p->child_storage.resize(f.children.size());
+    p->child_ptrs.resize(f.children.size());
+    for (size_t i = 0; i < f.children.size(); ++i) {
+        fill_schema(f.children[i], &p->child_storage[i]);
+        p->child_ptrs[i] = &p->child_storage[i];
+    }
+    out->format = p->format.c_str();
+    out->name = p->name.c_str();
+    out->metadata = p->metadata.empty() ? nullptr : p->metadata.data();
+    out->flags = f.nullable ? ARROW_FLAG_NULLABLE : 0;
+    out->n_children = int64_t(f.children.size());
+    out->children = p->child_ptrs.empty() ? nullptr : p->child_ptrs.data();
+    out->dictionary = nullptr;
+    out->release = release_schema;
+    out->private_data = p;
+}
+
+}  // namespace
+
+std::unique_ptr<AvroNode> parse_avro_schema(const char* json, size_t len) {
+    JsonReader rd(json, len);
+    Json doc = rd.parse_document();
+    return parse_node(doc, std::string(), 0);
+}
+
+bool is_supported(const AvroNode& top, std::string* why) {
+    if (top.k != AK::Record) {
+        if (why) *why = "top-level schema is not a record";
+        return false;
+    }
+    return supported_inner(top, why);
+}
+
+std::vector<ArrowField> to_arrow_fields(const AvroNode& top) {
+    std::vector<ArrowField> out;
+    if (top.k != AK::Record) throw std::runtime_error("top-level schema must be a record");
+    for (auto& f : top.fields) {
+        Props p = external_props(*f.type);
+        out.push_back(to_field(*f.type, &f.name, false, &p));
+    }
+    return out;
+}
+
+void export_arrow_schema(const std::vector<ArrowField>& fields, ArrowSchema* out) {
+    ArrowField top;
+    top.name = "";
+    top.type = AT::Struct;
+    top.nullable = false;
+    top.children = fields;
+    fill_schema(top, out);
+}
+
+}  // namespace rv

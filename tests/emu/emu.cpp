@@ -1,0 +1,163 @@
+// TEST INFRASTRUCTURE ONLY — host emulation of the GPU decode pipeline.
+//
+// Compiles the product's walker (pyruhvro_b200/csrc/walker.cuh), plan, layout and Arrow export
+// for the CPU and steps through the same count -> per-chunk scan -> exact layout -> emit ->
+// null-count sequence the kernels run, one 256-"lane" tile at a time.  It exists so the decode
+// LOGIC can be checked against the oracle in the GPU-less build container; it is never loaded by
+// the product (pyruhvro_b200 has no CPU path) and is not what the -m gpu tests exercise.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <cstdio>
+#include <stdexcept>
+#include <algorithm>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../pyruhvro_b200/csrc/plan.hpp"
+#include "../../pyruhvro_b200/csrc/result.hpp"
+#include "../../pyruhvro_b200/csrc/schema.hpp"
+#include "../../pyruhvro_b200/csrc/walker.cuh"
+
+using namespace rv;
+
+namespace {
+constexpr int kTile = 256;
+
+struct Tile { int chunk; int64_t r0; int nrec; int local; };
+
+std::vector<Tile> make_tiles(int64_t n, int k) {
+    std::vector<Tile> t;
+    const int64_t cr = n / k;
+    for (int j = 0; j < k; ++j) {
+        const int64_t cs = int64_t(j) * cr, ce = (j == k - 1) ? n : cs + cr;
+        int local = 0;
+        for (int64_t r = cs; r < ce; r += kTile) t.push_back(Tile{j, r, int(std::min<int64_t>(kTile, ce - r)), local++});
+    }
+    return t;
+}
+
+void init_ctx(WalkCtx& c, const Plan& plan, const uint8_t* data, const int64_t* off, const Tile& t, int lane,
+              uint32_t* cur, int S, void* const* bufs) {
+    std::memset(&c, 0, sizeof c);
+    c.nodes = plan.nodes.data();
+    c.cur = cur + lane;
+    c.cur_stride = kTile;
+    c.sym_off = plan.sym_off.data();
+    c.sym_bytes = plan.sym_bytes.data();
+    c.bufs = bufs;
+    c.in_range = lane < t.nrec;
+    c.row0 = uint32_t(t.local) * kTile + uint32_t(lane);
+    c.store_word = false;
+    (void)S;
+    if (c.in_range) {
+        const int64_t r = t.r0 + lane;
+        c.base = data + off[r];
+        c.pos = 0;
+        c.end = uint32_t(off[r + 1] - off[r]);
+    }
+}
+}  // namespace
+
+extern "C" {
+
+// Returns 0 on success; on a data error returns the error code and sets *err_record.
+// out_batches must have room for clamp_chunks(num_chunks, n) ArrowArrays.
+int emu_decode(const char* json, size_t len, const uint8_t* data, const int64_t* off, int64_t n, int64_t num_chunks,
+               ArrowArray* out_batches, ArrowSchema* out_schema, int64_t* k_out, int64_t* err_record, char* msg, size_t msg_cap) {
+    try {
+        auto avro = parse_avro_schema(json, len);
+        std::string why;
+        if (!is_supported(*avro, &why)) throw std::runtime_error("unsupported: " + why);
+        auto fields = to_arrow_fields(*avro);
+        auto plan_sp = std::make_shared<Plan>(build_plan(*avro, fields));
+        const Plan& plan = *plan_sp;
+        const int S = int(plan.streams.size()), S1 = std::max(S, 1);
+        const int k = int(clamp_chunks(num_chunks, n));
+        *k_out = k;
+        auto tiles = make_tiles(n, k);
+        std::vector<uint32_t> cur(size_t(S1) * kTile);
+        std::vector<std::vector<uint32_t>> tile_agg(tiles.size(), std::vector<uint32_t>(size_t(S1), 0));
+        // ---- count pass ----
+        for (size_t ti = 0; ti < tiles.size(); ++ti) {
+            std::fill(cur.begin(), cur.end(), 0u);
+            for (int lane = 0; lane < kTile; ++lane) {
+                WalkCtx c;
+                init_ctx(c, plan, data, off, tiles[ti], lane, cur.data(), S, nullptr);
+                walk_record<WM_COUNT>(c, int(plan.nodes.size()));
+                if (c.in_range && c.err) { *err_record = tiles[ti].r0 + lane; return int(c.err); }
+            }
+            for (int s = 0; s < S; ++s) {
+                uint64_t sum = 0;
+                for (int lane = 0; lane < kTile; ++lane) sum += cur[size_t(s) * kTile + lane];
+                if (sum > 0x7FFFFFFFull) { *err_record = tiles[ti].r0; return int(E_OVERFLOW); }
+                tile_agg[ti][size_t(s)] = uint32_t(sum);
+            }
+        }
+        // ---- per-chunk scan ----
+        std::vector<unsigned long long> chunk_tot(size_t(k) * size_t(S1), 0ull);
+        std::vector<std::vector<uint32_t>> tile_base(tiles.size(), std::vector<uint32_t>(size_t(S1), 0));
+        for (size_t ti = 0; ti < tiles.size(); ++ti)
+            for (int s = 0; s < S; ++s) {
+                unsigned long long& tot = chunk_tot[size_t(tiles[ti].chunk) * size_t(S1) + size_t(s)];
+                tile_base[ti][size_t(s)] = uint32_t(tot);
+                tot += tile_agg[ti][size_t(s)];
+                if (tot > 0x7FFFFFFFull) { *err_record = tiles[ti].r0; return int(E_OVERFLOW); }
+            }
+        // ---- layout + arena ----
+        Layout L = compute_layout(plan, n, k, chunk_tot.data());
+        struct Keep { std::shared_ptr<Plan> plan; std::vector<ChunkOut> chunks; uint8_t* arena; ~Keep() { std::free(arena); } };
+        auto keep = std::make_shared<Keep>();
+        keep->plan = plan_sp;
+        keep->arena = static_cast<uint8_t*>(std::calloc(std::max<size_t>(L.total_bytes, 64), 1));
+        // poison everything that the device does not zero, to catch missing writes
+        std::memset(keep->arena + L.zero_bytes, 0, L.total_bytes - L.zero_bytes);
+        const int n_slots = int(plan.slots.size());
+        std::vector<void*> bufs(size_t(k) * size_t(std::max(n_slots, 1)));
+        for (int j = 0; j < k; ++j)
+            for (int sl = 0; sl < n_slots; ++sl) bufs[size_t(j) * size_t(n_slots) + size_t(sl)] = keep->arena + L.chunks[size_t(j)].slot_off[size_t(sl)];
+        // ---- emit pass ----
+        for (size_t ti = 0; ti < tiles.size(); ++ti) {
+            const Tile& t = tiles[ti];
+            void* const* cb = bufs.data() + size_t(t.chunk) * size_t(n_slots);
+            std::fill(cur.begin(), cur.end(), 0u);
+            for (int lane = 0; lane < kTile; ++lane) {
+                WalkCtx c;
+                init_ctx(c, plan, data, off, t, lane, cur.data(), S, nullptr);
+                walk_record<WM_COUNT>(c, int(plan.nodes.size()));
+            }
+            for (int s = 0; s < S; ++s) {  // exclusive scan across lanes + tile base
+                uint32_t run = tile_base[ti][size_t(s)];
+                for (int lane = 0; lane < kTile; ++lane) { uint32_t v = cur[size_t(s) * kTile + lane]; cur[size_t(s) * kTile + lane] = run; run += v; }
+            }
+            if (t.local == 0)
+                for (const DNode& nd : plan.nodes)
+                    if (nd.kind == NK_STR || nd.kind == NK_ENUM || nd.kind == NK_LIST || nd.kind == NK_MAP) static_cast<int32_t*>(cb[nd.slot_a])[0] = 0;
+            for (int lane = 0; lane < kTile; ++lane) {
+                WalkCtx c;
+                init_ctx(c, plan, data, off, t, lane, cur.data(), S, cb);
+                walk_record<WM_EMIT>(c, int(plan.nodes.size()));
+            }
+        }
+        // ---- null counts ----
+        for (int j = 0; j < k; ++j)
+            for (int sl : plan.validity_slots) {
+                ChunkOut& c = L.chunks[size_t(j)];
+                const int64_t bits = c.space_rows[size_t(plan.slots[size_t(sl)].space)];
+                const uint8_t* bm = keep->arena + c.slot_off[size_t(sl)];
+                int64_t ones = 0;
+                for (int64_t i = 0; i < bits; ++i) ones += (bm[i >> 3] >> (i & 7)) & 1;
+                c.null_count[size_t(sl)] = bits - ones;
+            }
+        keep->chunks = L.chunks;
+        for (int j = 0; j < k; ++j) export_batch(plan, keep->chunks[size_t(j)], keep->arena, keep, &out_batches[j]);
+        if (out_schema) export_arrow_schema(fields, out_schema);
+        return 0;
+    } catch (const std::exception& e) {
+        std::snprintf(msg, msg_cap, "%s", e.what());
+        return -1;
+    }
+}
+
+}  // extern "C"

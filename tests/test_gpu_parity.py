@@ -1,0 +1,105 @@
+"""GPU parity: the CUDA path (through the C ABI, rv_decode_host / the pyruhvro Python surface)
+against the C oracle on the same bytes, buffer-for-buffer.  Needs a B200: `pytest -m gpu`."""
+import random
+
+import numpy as np
+import pytest
+
+import pyruhvro_b200 as pr
+from oracle import pyoracle as po
+from tests.golden import reference_datums as G
+from tests.parity import assert_matches_oracle, gen_case
+
+pytestmark = pytest.mark.gpu
+
+
+def test_goldens_values_and_buffers(coracle):
+    recs = [bytes.fromhex(h) for h in (G.G3_HEX, G.G4_HEX, G.G5_HEX)]
+    b = pr.deserialize_array(recs, G.G345_SCHEMA)
+    rows = b.to_pylist()
+    for got, want in zip(rows, G.G345_ROWS):
+        for key in ("name", "age", "emails", "address", "phone_numbers", "preferences", "status"):
+            assert got[key] == want[key], key
+    for sj, recs in [(G.G1_SCHEMA, [bytes.fromhex(G.G1_HEX)] * 4), (G.G2_SCHEMA, [bytes.fromhex(G.G2_HEX)]),
+                     (G.G345_SCHEMA, recs)]:
+        data, off = po.pack_records(recs)
+        for k in (1, 2, 8):
+            assert_matches_oracle(coracle, pr.deserialize_array_threaded(recs, sj, k), sj, data, off, len(recs), k)
+    g1 = pr.deserialize_array([bytes.fromhex(G.G1_HEX)] * 4, G.G1_SCHEMA)
+    assert g1.num_columns == 8 and g1.num_rows == 4       # deserialize.rs:248-249
+    assert g1.column("age").to_pylist() == [28] * 4
+    g2 = pr.deserialize_array([bytes.fromhex(G.G2_HEX)], G.G2_SCHEMA)
+    assert g2.to_pylist() == [G.G2_ROW]                    # deserialize.rs:307-308 (+ values)
+
+
+@pytest.mark.parametrize("seed", range(80))
+def test_random_schemas(coracle, seed):
+    rng = random.Random(1000 + seed)
+    n = rng.choice([1, 31, 32, 33, 255, 256, 257, 600, 2500])
+    sj, recs, data, off = gen_case(seed, n=n)
+    k = rng.choice([1, 1, 2, 3, 8, 1000])
+    assert_matches_oracle(coracle, pr.deserialize_array_threaded(recs, sj, k), sj, data, off, n, k)
+
+
+def test_packed_c_abi_path(coracle):
+    sj, recs, data, off = gen_case(7, n=5000)
+    assert_matches_oracle(coracle, pr.decode_packed(data, off, len(recs), sj, 8), sj, data, off, len(recs), 8)
+
+
+def test_empty_and_partition(coracle):
+    data, off = po.pack_records([])
+    b = pr.deserialize_array_threaded([], G.G345_SCHEMA, 8)
+    assert len(b) == 1 and b[0].num_rows == 0
+    assert_matches_oracle(coracle, b, G.G345_SCHEMA, data, off, 0, 8)
+    for n, k, sizes in [(10, 4, [2, 2, 2, 4]), (10, 0, [10]), (3, 8, [1, 1, 1]), (7, 7, [1] * 7)]:
+        sj, recs, data, off = gen_case(5, n=n)
+        b = pr.deserialize_array_threaded(recs, sj, k)
+        assert [x.num_rows for x in b] == sizes
+        assert_matches_oracle(coracle, b, sj, data, off, n, k)
+
+
+def test_malformed_inputs(coracle):
+    from tests import malformed as M
+    good = [M.good_record(i) for i in range(700)]
+    for name, code, bad in M.cases():
+        for pos in (0, 300, 699):
+            recs = list(good)
+            recs[pos] = bad
+            with pytest.raises(ValueError) as e:
+                pr.deserialize_array_threaded(recs, M.FLAT, 3)
+            assert f"(record {pos})" in str(e.value), (name, str(e.value))
+            with pytest.raises(po.DecodeError) as oe:
+                coracle.decode(M.FLAT, recs)
+            assert oe.value.record == pos
+    recs = [M.good_record(i) + b"junk" * (i % 3) for i in range(400)]  # trailing bytes ignored (:825-828)
+    data, off = po.pack_records(recs)
+    assert_matches_oracle(coracle, pr.deserialize_array_threaded(recs, M.FLAT, 2), M.FLAT, data, off, len(recs), 2)
+
+
+def test_error_surface():
+    with pytest.raises(TypeError):
+        pr.deserialize_array([b"ok", "not-bytes"], G.G1_SCHEMA)
+    with pytest.raises(ValueError):
+        pr.deserialize_array([b""], '{"type":"record","name":"B","fields":[{"name":"x","type":"bytes"}]}')  # no CPU fallback
+    with pytest.raises(ValueError):
+        pr.deserialize_array([b""], "{not json")
+
+
+def test_large_records_use_global_path(coracle):
+    """Records far larger than the shared-memory tile exercise the direct-from-global walk."""
+    sj = '{"type":"record","name":"L","fields":[{"name":"s","type":"string"},{"name":"a","type":{"type":"array","items":"long"}}]}'
+    s = po.parse_schema(sj)
+    rng = random.Random(9)
+    recs = [po.encode_datum(s, {"s": "x" * rng.choice([10, 5000, 70000]), "a": list(range(rng.choice([0, 3, 4000])))}) for _ in range(300)]
+    data, off = po.pack_records(recs)
+    assert_matches_oracle(coracle, pr.deserialize_array_threaded(recs, sj, 2), sj, data, off, len(recs), 2)
+
+
+def test_zero_width_items_and_deep_nesting(coracle):
+    sj = '{"type":"record","name":"Z","fields":[{"name":"z","type":{"type":"array","items":"null"}},' \
+         '{"name":"m","type":{"type":"map","values":{"type":"array","items":{"type":"array","items":["null","string"]}}}}]}'
+    s = po.parse_schema(sj)
+    rng = random.Random(3)
+    recs = [po.encode_datum(s, po.random_value(s, rng)) for _ in range(3000)]
+    data, off = po.pack_records(recs)
+    assert_matches_oracle(coracle, pr.deserialize_array_threaded(recs, sj, 2), sj, data, off, len(recs), 2)
