@@ -96,6 +96,10 @@ int64_t rv_result_num_rows(const rv_result* r, int64_t batch);
 /* Exact bytes of every Arrow buffer that is exported (the B_out of the roofline bookkeeping). */
 int64_t rv_result_arrow_bytes(const rv_result* r);
 
+/* Bytes of the result's buffer arena (what rv_result_to_host copies over PCIe; includes 64-byte
+ * padding and validity bitmaps that end up not being exported). */
+int64_t rv_result_buffer_bytes(const rv_result* r);
+
 /* Exports batch i as a struct array + (optionally, may be NULL) its schema through the Arrow C
  * Data Interface — what PyArrowType<RecordBatch> does at src/lib.rs:70,88.  Requires host buffers.
  * The exported array keeps the result's memory alive until its release callback runs. */

@@ -72,6 +72,8 @@ def _load():
     L.rv_result_num_rows.argtypes = [vp, i64]
     L.rv_result_arrow_bytes.restype = i64
     L.rv_result_arrow_bytes.argtypes = [vp]
+    L.rv_result_buffer_bytes.restype = i64
+    L.rv_result_buffer_bytes.argtypes = [vp]
     L.rv_result_export.argtypes = [vp, i64, vp, vp]
     L.rv_result_export_device.argtypes = [vp, i64, vp, vp]
     L.rv_result_free.argtypes = [vp]

@@ -578,6 +578,7 @@ int64_t rv_result_num_rows(const rv_result* r, int64_t batch) {
     return r->chunks[size_t(batch)].rows;
 }
 int64_t rv_result_arrow_bytes(const rv_result* r) { return r ? r->arrow_bytes : 0; }
+int64_t rv_result_buffer_bytes(const rv_result* r) { return r ? int64_t(r->arena->bytes) : 0; }
 
 rv_status rv_result_export(rv_result* r, int64_t batch, struct ArrowArray* out_array, struct ArrowSchema* out_schema) {
     if (!r || !out_array) return fail(RV_ERR_INVALID, "null argument");
