@@ -121,6 +121,21 @@ int rv_last_timings(float* out_ms, int cap);
 /* Number of kernels the last decode on this thread launched. */
 int rv_last_launch_count(void);
 
+/* Which record walker the last decode on this thread ran: "jit" (schema-specialised kernels compiled
+ * with NVRTC for the device's architecture) or "interp" (the statically compiled generic kernels).
+ * Both are GPU paths; RV_JIT=0 in the environment forces "interp". */
+const char* rv_last_walker(void);
+/* 1 / 0: use / do not use the schema-specialised kernels from now on; -1: follow the RV_JIT environment variable. */
+void rv_set_jit_enabled(int enabled);
+
+/* The generated CUDA C++ of the schema-specialised walker (diagnostics / tests).  Returns its length;
+ * copies at most cap-1 bytes + NUL into buf (buf may be NULL). */
+int64_t rv_schema_walker_source(const rv_schema* s, char* buf, size_t cap);
+
+/* Compiles the schema-specialised kernels for `arch` (e.g. "sm_100a") into the on-disk cubin cache
+ * (no GPU needed), so the first decode does not pay NVRTC latency. */
+rv_status rv_schema_precompile(const rv_schema* s, const char* arch);
+
 const char* rv_last_error(void);
 const char* rv_version(void);
 

@@ -84,12 +84,27 @@ def _load():
     L.rv_host_free.restype = None
     L.rv_last_timings.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_int]
     L.rv_last_launch_count.restype = ctypes.c_int
+    L.rv_last_walker.restype = cp
+    L.rv_set_jit_enabled.argtypes = [ctypes.c_int]
+    L.rv_set_jit_enabled.restype = None
+    L.rv_schema_walker_source.restype = i64
+    L.rv_schema_walker_source.argtypes = [vp, cp, ctypes.c_size_t]
+    L.rv_schema_precompile.argtypes = [vp, cp]
     L.rv_last_error.restype = cp
     L.rv_version.restype = cp
     return L
 
 
 lib = _load()
+
+
+def last_walker() -> str:
+    """"jit" or "interp": which GPU walker the last decode on this thread used."""
+    return (lib.rv_last_walker() or b"").decode()
+
+
+def set_jit_enabled(enabled: int) -> None:
+    lib.rv_set_jit_enabled(int(enabled))
 
 
 def _last_error() -> str:
@@ -119,6 +134,19 @@ class Schema:
     @property
     def is_supported(self) -> bool:
         return bool(lib.rv_schema_is_supported(self.handle))
+
+    def precompile(self, arch: str = "sm_100a") -> None:
+        """Compile the schema-specialised kernels into the on-disk cubin cache (no GPU needed)."""
+        _check(lib.rv_schema_precompile(self.handle, arch.encode()))
+
+    @property
+    def walker_source(self) -> str:
+        n = lib.rv_schema_walker_source(self.handle, None, 0)
+        if n < 0:
+            raise ValueError("schema has no decode plan")
+        buf = ctypes.create_string_buffer(n + 1)
+        lib.rv_schema_walker_source(self.handle, buf, n + 1)
+        return buf.value.decode()
 
     @property
     def arrow_schema(self) -> pa.Schema:

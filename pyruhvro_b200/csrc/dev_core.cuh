@@ -1,0 +1,338 @@
+// Device core of the record walk: byte access, wire primitives and per-type decode ops.
+//
+// These are the hand-written building blocks of BOTH walkers:
+//   * interp.cuh        — the generic lock-step interpreter over DNodes (statically compiled);
+//   * generated walkers — straight-line code emitted per schema by jit.cpp and compiled with
+//                         NVRTC for sm_100a (same ops, constants folded, no dispatch).
+// Each op restates one arm of the reference's FieldDecoder::decode / append_null
+// (ruhvro/src/fast_decode.rs:420-534) for a lane that either consumes bytes (`valid`) or appends
+// the null slot.  MODE: WM_COUNT accumulates per-stream contributions into cur[stream];
+// WM_EMIT writes Arrow buffers at the cursors the scans produced.
+//
+// Compiles for: nvcc (device), NVRTC (device), g++ (tests/emu host emulation; test infra only).
+#pragma once
+#include "dev_types.h"
+
+#if defined(__CUDACC__)
+#define RV_HD __host__ __device__ __forceinline__
+#else
+#define RV_HD inline
+#endif
+
+#if defined(__CUDACC__)
+extern __shared__ __align__(16) uint8_t rv_smem[];  // the CTA's dynamic shared memory (all regions)
+#endif
+
+namespace rv {
+
+enum WalkMode : int { WM_COUNT = 0, WM_EMIT = 1 };
+
+// SM = the record's bytes were staged into shared memory (device only).
+template <bool SM>
+struct WalkCtx {
+    static constexpr bool kShared = SM;
+    const uint8_t* base;   // global / host window holding this record (unused when SM)
+    uint32_t soff;         // SM: offset of the staged tile inside rv_smem
+    uint32_t pos, end;     // cursor / record end, relative to the window
+    uint32_t err;          // first error of this record
+    uint32_t pm;           // interpreter: presence by tree level
+    uint64_t usel;         // interpreter: selected variant per union nesting level (8 bits each)
+    const DNode* nodes;    // interpreter: the plan
+    uint32_t* cur;         // per-lane cursors: cur[stream * kBlock]
+    void* const* bufs;     // slot -> buffer of this chunk
+    const int32_t* sym_off;
+    const uint8_t* sym_bytes;
+    bool stage_on;         // emit: Utf8 bytes go to the shared-memory staging area
+    uint32_t stage_soff;   // offset of the staging area inside rv_smem
+    const uint32_t* stage_adj;  // [stream]: staging offset of the stream's region minus the tile base
+    uint32_t row0;         // chunk-local row of this record
+    bool in_range;         // the lane owns a record
+    bool store_word;       // space-0 bitmaps: this lane stores the warp's ballot word
+};
+
+template <class C>
+RV_HD void fail(C& c, uint32_t code) {
+    if (!c.err) c.err = code;
+}
+
+template <class C>
+RV_HD uint32_t ld_u8(const C& c, uint32_t pos) {
+#if defined(__CUDA_ARCH__)
+    if (C::kShared) return rv_smem[c.soff + pos];
+#endif
+    return c.base[pos];
+}
+
+RV_HD int64_t zz32(uint32_t r) { return int64_t(int32_t((r >> 1) ^ (0u - (r & 1u)))); }
+RV_HD int64_t zz64(uint64_t r) { return int64_t(r >> 1) ^ -int64_t(r & 1); }
+
+// read_zigzag_long (fast_decode.rs:854-869).  One-byte varints (branch indices, short lengths, small
+// ints: the bulk of real records) take a branch-light fast path; everything else goes through the
+// reference's byte loop.
+template <class C>
+RV_HD int64_t rd_varint(C& c) {
+    if (c.pos < c.end) {
+        const uint32_t b = ld_u8(c, c.pos);
+        if (b < 0x80u) { c.pos += 1; return zz32(b); }
+    }
+    uint64_t r = 0;
+    uint32_t shift = 0;
+    for (;;) {
+        if (c.pos >= c.end) { fail(c, E_EOF); return 0; }
+        const uint32_t b = ld_u8(c, c.pos++);
+        r |= uint64_t(b & 0x7Fu) << shift;
+        if (!(b & 0x80u)) break;
+        shift += 7;
+        if (shift >= 64) { fail(c, E_VARINT); return 0; }
+    }
+    return zz64(r);
+}
+
+// union_branch (fast_decode.rs:585-593): true = Value, false = Null (or error).
+template <class C>
+RV_HD bool rd_branch(C& c, bool null_first) {
+    if (c.pos < c.end) {
+        const uint32_t b = ld_u8(c, c.pos);
+        if (b == 0u || b == 2u) {  // canonical one-byte encodings of branch 0 / 1
+            c.pos += 1;
+            return (b == 2u) == null_first;
+        }
+    }
+    const int64_t idx = rd_varint(c);
+    if (c.err) return false;
+    if (idx == 0 || idx == 1) return (idx == 1) == null_first;
+    fail(c, E_BRANCH);
+    return false;
+}
+
+// Bit `row` of a validity / boolean buffer.  Space 0: rows are lane-aligned, so the warp ballots
+// and one lane stores a whole 32-bit word.  Deeper spaces: rows are lane-private cursors, so set
+// bits go through atomicOr into a zero-initialised buffer.
+template <int D, class C>
+RV_HD void put_bit(C& c, int slot, uint32_t row, bool bit) {
+#if defined(__CUDA_ARCH__)
+    if (D == 0) {
+        const unsigned w = __ballot_sync(0xFFFFFFFFu, bit);
+        if (c.store_word) static_cast<uint32_t*>(c.bufs[slot])[row >> 5] = w;
+    } else {
+        if (bit) atomicOr(static_cast<unsigned int*>(c.bufs[slot]) + (row >> 5), 1u << (row & 31));
+    }
+#else
+    if (bit && (D > 0 || c.in_range)) static_cast<uint8_t*>(c.bufs[slot])[row >> 3] |= uint8_t(1u << (row & 7));
+#endif
+}
+
+template <int D, class C>
+RV_HD bool may_store(const C& c) { return (D > 0) || c.in_range; }
+
+// ---- fixed-width leaves -------------------------------------------------------------------
+template <int MODE, int D, class C>
+RV_HD void op_i32(C& c, bool valid, int slot_a, int slot_v, uint32_t row) {
+    int32_t v = 0;
+    if (valid) { const int64_t x = rd_varint(c); if (!c.err) v = int32_t(x); else valid = false; }
+    if (MODE == WM_EMIT) {
+        if (may_store<D>(c)) static_cast<int32_t*>(c.bufs[slot_a])[row] = v;
+        if (slot_v >= 0) put_bit<D>(c, slot_v, row, valid);
+    }
+}
+
+template <int MODE, int D, class C>
+RV_HD void op_i64(C& c, bool valid, int slot_a, int slot_v, uint32_t row) {
+    int64_t v = 0;
+    if (valid) { const int64_t x = rd_varint(c); if (!c.err) v = x; else valid = false; }
+    if (MODE == WM_EMIT) {
+        if (may_store<D>(c)) static_cast<int64_t*>(c.bufs[slot_a])[row] = v;
+        if (slot_v >= 0) put_bit<D>(c, slot_v, row, valid);
+    }
+}
+
+template <int MODE, int D, class C>
+RV_HD void op_f32(C& c, bool valid, int slot_a, int slot_v, uint32_t row) {  // read_f32 :871-879
+    uint32_t v = 0;
+    if (valid) {
+        if (c.end - c.pos < 4u) { fail(c, E_EOF); valid = false; }
+        else {
+            if (MODE == WM_EMIT) {
+                const uint32_t p = c.pos;
+                v = ld_u8(c, p) | (ld_u8(c, p + 1) << 8) | (ld_u8(c, p + 2) << 16) | (ld_u8(c, p + 3) << 24);
+            }
+            c.pos += 4;
+        }
+    }
+    if (MODE == WM_EMIT) {
+        if (may_store<D>(c)) static_cast<uint32_t*>(c.bufs[slot_a])[row] = v;
+        if (slot_v >= 0) put_bit<D>(c, slot_v, row, valid);
+    }
+}
+
+template <int MODE, int D, class C>
+RV_HD void op_f64(C& c, bool valid, int slot_a, int slot_v, uint32_t row) {  // read_f64 :881-891
+    uint64_t v = 0;
+    if (valid) {
+        if (c.end - c.pos < 8u) { fail(c, E_EOF); valid = false; }
+        else {
+            if (MODE == WM_EMIT) {
+                const uint32_t p = c.pos;
+                const uint32_t lo = ld_u8(c, p) | (ld_u8(c, p + 1) << 8) | (ld_u8(c, p + 2) << 16) | (ld_u8(c, p + 3) << 24);
+                const uint32_t hi = ld_u8(c, p + 4) | (ld_u8(c, p + 5) << 8) | (ld_u8(c, p + 6) << 16) | (ld_u8(c, p + 7) << 24);
+                v = uint64_t(lo) | (uint64_t(hi) << 32);
+            }
+            c.pos += 8;
+        }
+    }
+    if (MODE == WM_EMIT) {
+        if (may_store<D>(c)) static_cast<uint64_t*>(c.bufs[slot_a])[row] = v;
+        if (slot_v >= 0) put_bit<D>(c, slot_v, row, valid);
+    }
+}
+
+template <int MODE, int D, class C>
+RV_HD void op_bool(C& c, bool valid, int slot_a, int slot_v, uint32_t row) {  // read_bool :893-900
+    bool v = false;
+    if (valid) {
+        if (c.pos >= c.end) { fail(c, E_EOF); valid = false; }
+        else {
+            const uint32_t b = ld_u8(c, c.pos++);
+            if (b > 1u) { fail(c, E_BOOL); valid = false; } else v = b != 0u;
+        }
+    }
+    if (MODE == WM_EMIT) {
+        put_bit<D>(c, slot_a, row, v);
+        if (slot_v >= 0) put_bit<D>(c, slot_v, row, valid);
+    }
+}
+
+// ---- Utf8 leaves ----------------------------------------------------------------------------
+// Destination of string bytes: the CTA's shared-memory staging area (written out with coalesced
+// 128-bit stores by the kernel afterwards) or, when the tile does not fit, global memory directly.
+template <class C>
+RV_HD void copy_from_record(C& c, int slot_b, int stream, uint32_t o, uint32_t s, uint32_t len) {
+#if defined(__CUDA_ARCH__)
+    if (c.stage_on) {
+        const uint32_t d = c.stage_soff + c.stage_adj[stream] + o;
+        for (uint32_t i = 0; i < len; ++i) rv_smem[d + i] = uint8_t(ld_u8(c, s + i));
+        return;
+    }
+#endif
+    (void)stream;
+    uint8_t* dst = static_cast<uint8_t*>(c.bufs[slot_b]) + o;
+    for (uint32_t i = 0; i < len; ++i) dst[i] = uint8_t(ld_u8(c, s + i));
+}
+
+template <class C>
+RV_HD void copy_from_symbols(C& c, int slot_b, int stream, uint32_t o, const uint8_t* src, uint32_t len) {
+#if defined(__CUDA_ARCH__)
+    if (c.stage_on) {
+        const uint32_t d = c.stage_soff + c.stage_adj[stream] + o;
+        for (uint32_t i = 0; i < len; ++i) rv_smem[d + i] = src[i];
+        return;
+    }
+#endif
+    (void)stream;
+    uint8_t* dst = static_cast<uint8_t*>(c.bufs[slot_b]) + o;
+    for (uint32_t i = 0; i < len; ++i) dst[i] = src[i];
+}
+
+template <int MODE, int D, class C>
+RV_HD void utf8_finish(C& c, bool valid, uint32_t len, int slot_a, int slot_v, int stream, uint32_t row) {
+    uint32_t& cur = c.cur[uint32_t(stream) * kBlock];
+    if (MODE == WM_COUNT) {
+        const uint32_t nxt = cur + len;
+        if (nxt < cur) fail(c, E_OVERFLOW);
+        cur = nxt;
+    } else {
+        const uint32_t o = cur + len;
+        if (may_store<D>(c)) static_cast<int32_t*>(c.bufs[slot_a])[row + 1] = int32_t(o);
+        cur = o;
+        if (slot_v >= 0) put_bit<D>(c, slot_v, row, valid);
+    }
+}
+
+template <int MODE, int D, class C>
+RV_HD void op_str(C& c, bool valid, int slot_a, int slot_b, int slot_v, int stream, uint32_t row) {  // read_string :902-922
+    uint32_t len = 0;
+    if (valid) {
+        const int64_t l = rd_varint(c);
+        if (c.err) valid = false;
+        else if (l < 0) { fail(c, E_NEG_LEN); valid = false; }
+        else if (uint64_t(l) > uint64_t(c.end - c.pos)) { fail(c, E_EOF); valid = false; }
+        else {
+            len = uint32_t(l);
+            if (MODE == WM_EMIT) copy_from_record(c, slot_b, stream, c.cur[uint32_t(stream) * kBlock], c.pos, len);
+            c.pos += len;
+        }
+    }
+    utf8_finish<MODE, D>(c, valid, len, slot_a, slot_v, stream, row);
+}
+
+template <int MODE, int D, class C>
+RV_HD void op_enum(C& c, bool valid, int slot_a, int slot_b, int slot_v, int stream, uint32_t row, int sym_base, int n_sym) {  // append_enum :570-578
+    uint32_t len = 0;
+    if (valid) {
+        const int64_t l = rd_varint(c);
+        if (c.err) valid = false;
+        else if (uint64_t(l) >= uint64_t(uint32_t(n_sym))) { fail(c, E_ENUM); valid = false; }
+        else {
+            const int32_t b0 = c.sym_off[sym_base + int32_t(l)];
+            len = uint32_t(c.sym_off[sym_base + int32_t(l) + 1] - b0);
+            if (MODE == WM_EMIT) copy_from_symbols(c, slot_b, stream, c.cur[uint32_t(stream) * kBlock], c.sym_bytes + b0, len);
+        }
+    }
+    utf8_finish<MODE, D>(c, valid, len, slot_a, slot_v, stream, row);
+}
+
+// ---- containers -------------------------------------------------------------------------------
+// N-variant union head (UnionDecoder::decode / append_null :643-668): returns the selected variant
+// (-1: the union itself is absent -> every child appends null, type_id 0).
+template <int MODE, int D, class C>
+RV_HD int op_union(C& c, bool valid, int n_variants, int slot_a, uint32_t row) {
+    int sel = -1;
+    if (valid) {
+        const int64_t idx = rd_varint(c);
+        if (!c.err) {
+            if (idx < 0 || idx >= int64_t(n_variants)) fail(c, E_BRANCH);
+            else sel = int(idx);
+        }
+    }
+    if (MODE == WM_EMIT && may_store<D>(c)) static_cast<int8_t*>(c.bufs[slot_a])[row] = int8_t(sel < 0 ? 0 : sel);
+    return sel;
+}
+
+// read_block_count (:689-700) inside the item loop of ListDecoder / MapDecoder (:703-719,745-762).
+// Returns 0: list ended or error (leave the loop); 1: `rem` items follow; 2: a zero-width block was
+// folded into `total` (read the next block header).
+template <class C>
+RV_HD int rd_block(C& c, int64_t& rem, uint32_t& total, bool zero_items) {
+    int64_t n = rd_varint(c);
+    if (c.err) return 0;
+    if (n < 0) {
+        (void)rd_varint(c);  // block byte size: ignored, the items are always walked
+        if (c.err) return 0;
+        n = int64_t(0 - uint64_t(n));
+        if (n < 0) return 2;  // i64::MIN: `0..n` is an empty range in the reference
+    }
+    if (n == 0) return 0;
+    if (zero_items) {  // items are zero bytes wide and own no buffers: no need to iterate
+        if (n > int64_t(0x7FFFFFFF) - int64_t(total)) { fail(c, E_OVERFLOW); return 0; }
+        total += uint32_t(n);
+        return 2;
+    }
+    rem = n;
+    return 1;
+}
+
+template <int MODE, int D, class C>
+RV_HD void list_finish(C& c, bool valid, uint32_t first_row, uint32_t total, int slot_a, int slot_v, int stream, uint32_t row) {
+    uint32_t& cur = c.cur[uint32_t(stream) * kBlock];
+    if (MODE == WM_COUNT) {
+        const uint32_t nxt = cur + total;
+        if (nxt < cur || nxt > 0x7FFFFFFFu) fail(c, E_OVERFLOW);
+        cur = nxt;
+    } else {
+        cur = first_row + total;
+        if (may_store<D>(c)) static_cast<int32_t*>(c.bufs[slot_a])[row + 1] = int32_t(first_row + total);
+        if (slot_v >= 0) put_bit<D>(c, slot_v, row, valid);
+    }
+}
+
+}  // namespace rv

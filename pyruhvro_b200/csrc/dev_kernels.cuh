@@ -1,0 +1,256 @@
+// Kernel bodies of the decode, templated over the walker (InterpWalker or a generated,
+// schema-specialised walker).  Device-only; compiled by nvcc (kernels.cu) and by NVRTC (jit.cpp).
+//
+//   count_body  one CTA per 256-record tile: stage the tile's contiguous byte window in shared
+//               memory (coalesced 128-bit loads), COUNT-walk every record (full validation),
+//               CTA-reduce per-stream totals -> tile_agg.
+//   emit_body   same staging; COUNT walk -> CTA-wide exclusive scan of the lane counts (+ the tile's
+//               base from scan_kernel) -> EMIT walk.  Utf8 bytes are assembled per column in a
+//               shared-memory staging area and written out with coalesced 128-bit stores; fixed-width
+//               values / offsets are stored row-aligned; space-0 validity is one ballot word per warp.
+//
+// Shared-memory map (dynamic, rv_smem):
+//   [nodes n_nodes*32][cur S*256*4][wtot S*8*4][tot (S+1)*4][adj S*4][in: smem_data_cap][out: smem_stage_cap]
+#pragma once
+#include "dev_core.cuh"
+
+namespace rv {
+
+struct Tile {
+    int chunk;
+    int local_tile;
+    int64_t r0;          // first record of the tile
+    int nrec;            // records in the tile
+    int64_t chunk_len;   // rows in the chunk
+};
+
+__device__ __forceinline__ Tile tile_of(const DecodeParams& p, int tile) {
+    Tile t;
+    int j = tile / p.tiles_per_chunk;
+    if (j > p.k - 1) j = p.k - 1;
+    t.chunk = j;
+    t.local_tile = tile - j * p.tiles_per_chunk;
+    const int64_t cs = int64_t(j) * p.chunk_rows;
+    const int64_t ce = (j == p.k - 1) ? p.n : cs + p.chunk_rows;
+    t.chunk_len = ce - cs;
+    t.r0 = cs + int64_t(t.local_tile) * kBlock;
+    const int64_t left = ce - t.r0;
+    t.nrec = left < kBlock ? int(left) : kBlock;
+    return t;
+}
+
+struct TileWindow {
+    bool staged;
+    int64_t t0, t1;   // byte range of the tile in `data`
+    uint32_t mis;     // (data + t0) & 15: the window starts at the aligned-down address
+};
+
+// Loads the plan and the tile's byte window into shared memory.
+__device__ __forceinline__ TileWindow stage_in(const DecodeParams& p, const Tile& t, const SmemMap& m) {
+    const int tid = threadIdx.x;
+    if (p.n_nodes) {
+        uint4* dn = reinterpret_cast<uint4*>(rv_smem + m.nodes);
+        for (int i = tid; i < p.n_nodes * 2; i += kBlock) dn[i] = __ldg(reinterpret_cast<const uint4*>(p.nodes) + i);
+    }
+    uint32_t* cur = reinterpret_cast<uint32_t*>(rv_smem + m.cur);
+    for (int s = 0; s < p.n_streams; ++s) cur[s * kBlock + tid] = 0;
+    TileWindow w;
+    w.t0 = __ldg(p.offsets + t.r0);
+    w.t1 = __ldg(p.offsets + t.r0 + t.nrec);
+    const int64_t span = w.t1 - w.t0;
+    w.mis = uint32_t(reinterpret_cast<uintptr_t>(p.data + w.t0) & 15u);
+    w.staged = span >= 0 && uint64_t(span) + w.mis <= uint64_t(p.smem_data_cap);
+    if (w.staged) {
+        const uint4* g = reinterpret_cast<const uint4*>(p.data + w.t0 - w.mis);
+        const int nvec = int((span + w.mis + 15) >> 4);
+        uint4* d = reinterpret_cast<uint4*>(rv_smem + m.in);
+        for (int i = tid; i < nvec; i += kBlock) d[i] = __ldg(g + i);
+    }
+    return w;
+}
+
+template <class C>
+__device__ __forceinline__ int64_t init_ctx(C& c, const DecodeParams& p, const Tile& t, const SmemMap& m, const TileWindow& w) {
+    const int tid = threadIdx.x;
+    c.nodes = reinterpret_cast<const DNode*>(rv_smem + m.nodes);
+    c.cur = reinterpret_cast<uint32_t*>(rv_smem + m.cur) + tid;
+    c.sym_off = p.sym_off;
+    c.sym_bytes = p.sym_bytes;
+    c.bufs = p.bufs ? p.bufs + size_t(t.chunk) * p.n_slots : nullptr;
+    c.err = 0;
+    c.pm = 0;
+    c.usel = 0;
+    c.stage_on = false;
+    c.stage_soff = m.out;
+    c.stage_adj = reinterpret_cast<const uint32_t*>(rv_smem + m.adj);
+    c.in_range = tid < t.nrec;
+    c.row0 = uint32_t(t.local_tile) * kBlock + tid;
+    c.store_word = (tid & 31) == 0 && int64_t(c.row0) < t.chunk_len;
+    c.base = p.data;
+    c.soff = m.in;
+    c.pos = c.end = 0;
+    const int64_t r = t.r0 + tid;
+    if (c.in_range) {
+        const int64_t o0 = __ldg(p.offsets + r), o1 = __ldg(p.offsets + r + 1);
+        if (o1 < o0 || o1 - o0 > int64_t(0xFFFFFFF0u)) c.err = E_OVERFLOW;  // malformed offsets / >4 GiB record
+        else if (C::kShared) {
+            if (o0 < w.t0 || o1 > w.t1) c.err = E_OVERFLOW;
+            else { c.pos = uint32_t(o0 - w.t0) + w.mis; c.end = uint32_t(o1 - w.t0) + w.mis; }
+        } else {
+            c.base = p.data + o0;
+            c.end = uint32_t(o1 - o0);
+        }
+    }
+    return r;
+}
+
+__device__ __forceinline__ void report(const DecodeParams& p, int64_t record, uint32_t code) {
+    atomicMin(p.err, (static_cast<unsigned long long>(record) << 8) | code);
+}
+
+// ---- count ----------------------------------------------------------------------------------
+template <class W, bool SM>
+__device__ __forceinline__ void count_walk(const DecodeParams& p, const Tile& t, const SmemMap& m, const TileWindow& w) {
+    WalkCtx<SM> c;
+    const int64_t r = init_ctx(c, p, t, m, w);
+    W::template walk<WM_COUNT>(c, p.n_nodes);
+    if (c.in_range && c.err) report(p, r, c.err);
+}
+
+// GENERIC = the walker can read records straight from global memory (interpreter).  A specialised
+// walker is only instantiated for the shared-memory window; tiles that do not fit are handed to the
+// interpreter kernels through p.overflow.
+template <class W, bool GENERIC>
+__device__ __forceinline__ void count_body(const DecodeParams& p, const int tile_id) {
+    const Tile t = tile_of(p, tile_id);
+    const SmemMap m = smem_map(p.n_nodes, p.n_streams, p.smem_data_cap);
+    const TileWindow w = stage_in(p, t, m);
+    __syncthreads();
+    if (w.staged) count_walk<W, true>(p, t, m, w);
+    else if constexpr (GENERIC) count_walk<W, false>(p, t, m, w);
+    else {
+        if (threadIdx.x == 0) p.overflow[1 + atomicAdd(p.overflow, 1)] = tile_id;
+        return;  // uniform: the whole CTA leaves
+    }
+    __syncthreads();
+    const uint32_t* cur = reinterpret_cast<const uint32_t*>(rv_smem + m.cur);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int s = warp; s < p.n_streams; s += kWarps) {
+        unsigned long long sum = 0;
+        for (int i = lane; i < kBlock; i += 32) sum += cur[s * kBlock + i];
+        for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+        if (lane == 0) {
+            if (sum > 0x7FFFFFFFull) { report(p, t.r0, E_OVERFLOW); sum = 0x7FFFFFFFull; }
+            p.tile_agg[size_t(s) * p.n_tiles + tile_id] = uint32_t(sum);
+        }
+    }
+}
+
+// ---- emit -----------------------------------------------------------------------------------
+template <class W, bool SM>
+__device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t, const int tile_id, const SmemMap& m, const TileWindow& w) {
+    WalkCtx<SM> c;
+    (void)init_ctx(c, p, t, m, w);
+    const uint32_t pos0 = c.pos;
+    W::template walk<WM_COUNT>(c, p.n_nodes);
+    const uint32_t count_err = c.err;
+    __syncthreads();
+
+    // CTA-wide exclusive scan of every stream's lane counts.
+    uint32_t* cur = reinterpret_cast<uint32_t*>(rv_smem + m.cur);
+    uint32_t* wtot = reinterpret_cast<uint32_t*>(rv_smem + m.wtot);
+    uint32_t* tot = reinterpret_cast<uint32_t*>(rv_smem + m.tot);
+    uint32_t* adj = reinterpret_cast<uint32_t*>(rv_smem + m.adj);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int s = 0; s < p.n_streams; ++s) {
+        const uint32_t v = cur[s * kBlock + tid];
+        uint32_t incl = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += u;
+        }
+        if (lane == 31) wtot[s * kWarps + warp] = incl;
+        cur[s * kBlock + tid] = incl - v;
+    }
+    __syncthreads();
+    // Tile totals and the staging map of the Utf8 streams.  Stream s's bytes of this tile occupy
+    // [tile_base, tile_base + tot) of its Arrow data buffer; in shared memory its region starts at an
+    // offset congruent (mod 16) to the global destination so the write-out can use aligned uint4.
+    if (tid == 0) {
+        uint32_t off = 0;
+        bool fits = p.smem_stage_cap > 0;
+        for (int s = 0; s < p.n_streams; ++s) {
+            uint32_t tt = 0;
+            for (int ww = 0; ww < kWarps; ++ww) tt += wtot[s * kWarps + ww];
+            tot[s] = tt;
+            const int slot = p.stream_slot[s];
+            if (slot >= 0) {
+                const uint32_t tb = p.tile_base[size_t(s) * p.n_tiles + tile_id];
+                const uint32_t galign = uint32_t(reinterpret_cast<uintptr_t>(static_cast<uint8_t*>(c.bufs[slot]) + tb) & 15u);
+                const uint32_t start = ((off + 15u) & ~15u) + galign;
+                adj[s] = start - tb;  // staging offset of byte `o` (chunk-relative) = adj + o
+                off = start + tt;
+                if (off > p.smem_stage_cap) fits = false;
+            } else {
+                adj[s] = 0;
+            }
+        }
+        tot[p.n_streams] = fits ? 1u : 0u;  // tot has S+1 entries
+    }
+    __syncthreads();
+    const bool stage_on = p.n_streams > 0 && tot[p.n_streams] != 0;
+    for (int s = 0; s < p.n_streams; ++s) {
+        uint32_t b = __ldg(p.tile_base + size_t(s) * p.n_tiles + tile_id);
+        for (int ww = 0; ww < warp; ++ww) b += wtot[s * kWarps + ww];
+        cur[s * kBlock + tid] += b;
+    }
+    // offsets[0] = 0 of every offsets buffer of this chunk (first tile of the chunk only)
+    if (t.local_tile == 0) {
+        if (p.n_nodes) {
+            for (int i = tid; i < p.n_nodes; i += kBlock) {
+                const DNode nd = c.nodes[i];
+                if (nd.kind == NK_STR || nd.kind == NK_ENUM || nd.kind == NK_LIST || nd.kind == NK_MAP)
+                    static_cast<int32_t*>(c.bufs[nd.slot_a])[0] = 0;
+            }
+        } else {
+            W::zero_offsets(c, tid);
+        }
+    }
+    c.pos = pos0;
+    c.err = count_err;  // a record that failed validation emits only null slots
+    c.stage_on = stage_on;
+    W::template walk<WM_EMIT>(c, p.n_nodes);
+
+    if (stage_on) {  // coalesced write-out of the staged Utf8 bytes, one warp per stream at a time
+        __syncthreads();
+        for (int s = warp; s < p.n_streams; s += kWarps) {
+            const int slot = p.stream_slot[s];
+            const uint32_t n = tot[s];
+            if (slot < 0 || n == 0) continue;
+            const uint32_t tb = __ldg(p.tile_base + size_t(s) * p.n_tiles + tile_id);
+            uint8_t* g = static_cast<uint8_t*>(c.bufs[slot]) + tb;
+            const uint32_t so = m.out + adj[s] + tb;  // rv_smem offset of the region's first byte
+            const uint32_t head = min(n, (16u - uint32_t(reinterpret_cast<uintptr_t>(g) & 15u)) & 15u);
+            for (uint32_t i = lane; i < head; i += 32) g[i] = rv_smem[so + i];
+            const uint32_t nvec = (n - head) >> 4;
+            const uint4* sv = reinterpret_cast<const uint4*>(rv_smem + so + head);
+            uint4* gv = reinterpret_cast<uint4*>(g + head);
+            for (uint32_t i = lane; i < nvec; i += 32) gv[i] = sv[i];
+            const uint32_t done = head + (nvec << 4);
+            for (uint32_t i = done + lane; i < n; i += 32) g[i] = rv_smem[so + i];
+        }
+    }
+}
+
+template <class W, bool GENERIC>
+__device__ __forceinline__ void emit_body(const DecodeParams& p, const int tile_id) {
+    const Tile t = tile_of(p, tile_id);
+    const SmemMap m = smem_map(p.n_nodes, p.n_streams, p.smem_data_cap);
+    const TileWindow w = stage_in(p, t, m);
+    __syncthreads();
+    if (w.staged) emit_walks<W, true>(p, t, tile_id, m, w);
+    else if constexpr (GENERIC) emit_walks<W, false>(p, t, tile_id, m, w);
+    // else: the tile is on the overflow list and the interpreter pass emits it
+}
+
+}  // namespace rv

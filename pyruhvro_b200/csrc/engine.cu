@@ -19,6 +19,7 @@
 
 #include "../../include/ruhvro_b200.h"
 #include "arrow_c.h"
+#include "jit.hpp"
 #include "kernels.cuh"
 #include "plan.hpp"
 #include "result.hpp"
@@ -34,6 +35,7 @@ namespace {
 thread_local std::string t_error;
 thread_local float t_timings[6] = {0, 0, 0, 0, 0, 0};
 thread_local int t_launches = 0;
+thread_local const char* t_walker = "none";
 
 rv_status fail(rv_status st, const std::string& msg) {
     t_error = msg;
@@ -157,6 +159,16 @@ struct DevicePlan {
     DNode* nodes = nullptr;
     int32_t* sym_off = nullptr;
     uint8_t* sym_bytes = nullptr;
+    int16_t* stream_slot = nullptr;
+};
+
+// Schema-specialised kernels (NVRTC), shared by all devices of the process.
+struct JitState {
+    bool tried = false;
+    bool ok = false;
+    std::string status = "not compiled";
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t count = nullptr, emit = nullptr;
 };
 
 struct rv_schema {
@@ -170,6 +182,7 @@ struct rv_schema {
     bool has_plan = false;
     std::mutex mu;
     std::map<int, DevicePlan> dev;  // device id -> uploaded plan
+    JitState jit;
 };
 
 namespace {
@@ -183,12 +196,58 @@ rv_status device_plan(rv_schema* s, int device, DevicePlan* out) {
     RV_CUDA(cudaMalloc(&d.nodes, std::max<size_t>(1, p.nodes.size()) * sizeof(DNode)));
     RV_CUDA(cudaMalloc(&d.sym_off, std::max<size_t>(1, p.sym_off.size()) * 4));
     RV_CUDA(cudaMalloc(&d.sym_bytes, std::max<size_t>(1, p.sym_bytes.size())));
+    std::vector<int16_t> sslot(std::max<size_t>(1, p.streams.size()), int16_t(-1));
+    for (size_t i = 0; i < p.streams.size(); ++i)
+        if (!p.streams[i].is_rows) sslot[i] = p.nodes[size_t(p.streams[i].node)].slot_b;
+    RV_CUDA(cudaMalloc(&d.stream_slot, sslot.size() * 2));
+    RV_CUDA(cudaMemcpy(d.stream_slot, sslot.data(), sslot.size() * 2, cudaMemcpyHostToDevice));
     RV_CUDA(cudaMemcpy(d.nodes, p.nodes.data(), p.nodes.size() * sizeof(DNode), cudaMemcpyHostToDevice));
     if (!p.sym_off.empty()) RV_CUDA(cudaMemcpy(d.sym_off, p.sym_off.data(), p.sym_off.size() * 4, cudaMemcpyHostToDevice));
     if (!p.sym_bytes.empty()) RV_CUDA(cudaMemcpy(d.sym_bytes, p.sym_bytes.data(), p.sym_bytes.size(), cudaMemcpyHostToDevice));
     s->dev[device] = d;
     *out = d;
     return RV_OK;
+}
+
+constexpr int kOverflowGrid = 592;  // 4 CTAs per SM striding over the (normally empty) overflow list
+
+std::atomic<int> g_jit_override{-1};  // -1: follow RV_JIT; 0/1: rv_set_jit_enabled()
+
+bool jit_enabled() {
+    const int o = g_jit_override.load(std::memory_order_relaxed);
+    if (o >= 0) return o != 0;
+    const char* e = std::getenv("RV_JIT");
+    return !(e && e[0] == '0');
+}
+
+std::string device_arch(int device) {
+    if (const char* e = std::getenv("RV_JIT_ARCH")) return e;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return "sm_100a";
+    return "sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ((prop.major >= 9) ? "a" : "");
+}
+
+// Compiles + loads the schema-specialised kernels once per schema.  On any failure the generic
+// interpreter kernels (also on the GPU) are used and the reason is kept in jit.status.
+const JitState& ensure_jit(rv_schema* s, int device) {
+    static const JitState disabled = [] { JitState d; d.tried = true; d.status = "disabled (RV_JIT=0 / rv_set_jit_enabled(0))"; return d; }();
+    if (!jit_enabled()) return disabled;
+    std::lock_guard<std::mutex> g(s->mu);
+    JitState& j = s->jit;
+    if (j.tried) return j;
+    j.tried = true;
+    std::vector<char> cubin;
+    std::string log;
+    if (!jit_cubin(generate_kernel_source(s->plan), device_arch(device), &cubin, &log)) { j.status = "NVRTC: " + log; return j; }
+    cudaError_t e = cudaLibraryLoadData(&j.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&j.count, j.lib, "rvj_count");
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&j.emit, j.lib, "rvj_emit");
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(reinterpret_cast<const void*>(j.count), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(reinterpret_cast<const void*>(j.emit), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { j.status = std::string("loading the compiled walker failed: ") + cudaGetErrorString(e); (void)cudaGetLastError(); return j; }
+    j.ok = true;
+    j.status = "ok";
+    return j;
 }
 
 }  // namespace
@@ -265,11 +324,15 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
 
     std::vector<unsigned long long> chunk_tot(size_t(k) * size_t(std::max(S, 1)), 0ull);
     DecodeParams p{};
-    DevBuf tile_agg, tile_base, d_chunk_tot, d_err, d_bufs;
+    DevBuf tile_agg, tile_base, d_chunk_tot, d_err, d_bufs, d_overflow;
+    DecodeParams pi{};   // interpreter pass over the tiles the specialised kernels skipped
+    size_t smem_interp = 0;
     cudaEvent_t ev[8];
     for (auto& e : ev) RV_CUDA(cudaEventCreate(&e));
     struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 8; ++i) cudaEventDestroy(e[i]); } } evg{ev};
-    size_t smem = 0;
+    size_t smem_count = 0, smem_emit = 0;
+    bool use_jit = false;
+    cudaKernel_t jit_count = nullptr, jit_emit = nullptr;
 
     if (n > 0) {
         DevicePlan dp;
@@ -288,29 +351,45 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
             RV_CUDA(cudaStreamSynchronize(stream));
             total_bytes = ends[1] - ends[0];
         }
-        // shared-memory budget: plan + cursors are fixed; the rest stages the tile's bytes
-        const size_t fixed = decode_smem_bytes(int(plan.nodes.size()), S, 0);
+        // Walker: schema-specialised (NVRTC) when available, else the generic interpreter.
+        const JitState& jit = ensure_jit(s, device);
+        use_jit = jit.ok;
+        jit_count = jit.count;
+        jit_emit = jit.emit;
+        t_walker = use_jit ? "jit" : "interp";
+        const int plan_nodes = use_jit ? 0 : int(plan.nodes.size());  // the generated walker has the plan baked in
+        // shared-memory budget: [plan +] cursors are fixed; then the tile's input bytes; then (emit) the
+        // staging area in which the tile's Utf8 output is assembled for coalesced write-out
+        const size_t fixed = smem_map(plan_nodes, S, 0).in;
         const size_t limit = 227 * 1024;
-        if (fixed + 1024 > limit) return fail(RV_ERR_SCHEMA, "schema too wide for the shared-memory cursor table");
+        if (fixed + 2048 > limit) return fail(RV_ERR_SCHEMA, "schema too wide for the shared-memory cursor table");
         const double avg = total_bytes > 0 ? double(total_bytes) / double(n) : 16.0;
         size_t want = size_t(avg * kBlock * 1.25) + 1024;
         want = (want + 1023) & ~size_t(1023);
-        want = std::max<size_t>(want, 8192);
-        const size_t room = (limit - fixed) & ~size_t(15);
-        // prefer >= 2 CTAs per SM when the tile fits in half the shared memory
-        const size_t half = (limit / 2 > fixed + 4096) ? ((limit / 2 - fixed) & ~size_t(15)) : 0;
-        size_t cap = want <= half ? want : std::min(want, room);
-        smem = fixed + cap;
-
+        want = std::max<size_t>(want, 4096);
+        const size_t room = (limit - fixed - 64) & ~size_t(15);
+        size_t cap_in = std::min(want, room);
+        size_t cap_out = 0;
+        bool any_bytes = false;
+        for (const Stream& st_ : plan.streams) any_bytes |= !st_.is_rows;
+        if (any_bytes && room > cap_in + 1024) cap_out = std::min(want + 256, (room - cap_in) & ~size_t(15));
+        if (const char* e = std::getenv("RV_NO_STAGE_OUT")) if (e[0] == '1') cap_out = 0;
+        smem_count = smem_map(plan_nodes, S, uint32_t(cap_in)).out;
+        smem_emit = smem_count + cap_out;
+        p.smem_stage_cap = uint32_t(cap_out);
+        p.stream_slot = dp.stream_slot;
+        const int n_nodes_param = plan_nodes;
         p.data = d_data; p.offsets = d_offsets; p.n = n; p.chunk_rows = chunk_rows; p.k = k;
         p.tiles_per_chunk = int32_t(tpc); p.n_tiles = int32_t(n_tiles);
-        p.nodes = dp.nodes; p.n_nodes = int32_t(plan.nodes.size()); p.n_streams = S; p.n_slots = n_slots;
+        p.nodes = dp.nodes; p.n_nodes = int32_t(n_nodes_param); p.n_streams = S; p.n_slots = n_slots;
         p.sym_off = dp.sym_off; p.sym_bytes = dp.sym_bytes;
-        p.smem_data_cap = uint32_t(cap);
+        p.smem_data_cap = uint32_t(cap_in);
         RV_CUDA(tile_agg.alloc(size_t(std::max(S, 1)) * size_t(n_tiles) * 4, stream));
         RV_CUDA(tile_base.alloc(size_t(std::max(S, 1)) * size_t(n_tiles) * 4, stream));
         RV_CUDA(d_chunk_tot.alloc(chunk_tot.size() * 8, stream));
         RV_CUDA(d_err.alloc(8, stream));
+        RV_CUDA(d_overflow.alloc((size_t(n_tiles) + 1) * 4, stream));
+        RV_CUDA(cudaMemsetAsync(d_overflow.p, 0, 4, stream));
         p.tile_agg = static_cast<uint32_t*>(tile_agg.p);
         p.tile_base = static_cast<uint32_t*>(tile_base.p);
         p.chunk_tot = static_cast<unsigned long long*>(d_chunk_tot.p);
@@ -319,7 +398,22 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         RV_CUDA(cudaMemsetAsync(d_err.p, 0xFF, 8, stream));
 
         RV_CUDA(cudaEventRecord(ev[0], stream));
-        launch_count(p, smem, stream);
+        p.tile_list = nullptr;
+        p.overflow = static_cast<int32_t*>(d_overflow.p);
+        if (use_jit) {
+            void* args[] = {&p};
+            RV_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(jit_count), dim3(unsigned(p.n_tiles)), dim3(kBlock), args, smem_count, stream));
+            pi = p;
+            pi.n_nodes = int32_t(plan.nodes.size());
+            pi.tile_list = static_cast<const int32_t*>(d_overflow.p) + 1;
+            pi.smem_stage_cap = 0;
+            pi.smem_data_cap = uint32_t(std::min<size_t>(cap_in, (limit - smem_map(pi.n_nodes, S, 0).in - 64) & ~size_t(15)));
+            smem_interp = smem_map(pi.n_nodes, S, pi.smem_data_cap).out;
+            launch_count(pi, kOverflowGrid, smem_interp, stream);
+            t_launches += 1;
+        } else {
+            launch_count(p, p.n_tiles, smem_count, stream);
+        }
         RV_CUDA(cudaEventRecord(ev[1], stream));
         launch_scan(p, stream);
         RV_CUDA(cudaEventRecord(ev[2], stream));
@@ -355,7 +449,15 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         p.bufs = static_cast<void* const*>(d_bufs.p);
 
         RV_CUDA(cudaEventRecord(ev[3], stream));
-        launch_emit(p, smem, stream);
+        if (use_jit) {
+            void* args[] = {&p};
+            RV_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(jit_emit), dim3(unsigned(p.n_tiles)), dim3(kBlock), args, smem_emit, stream));
+            pi.bufs = p.bufs;
+            launch_emit(pi, kOverflowGrid, smem_interp, stream);
+            t_launches += 1;
+        } else {
+            launch_emit(p, p.n_tiles, smem_emit, stream);
+        }
         RV_CUDA(cudaEventRecord(ev[4], stream));
         RV_CUDA(cudaGetLastError());
         t_launches += 1;
@@ -639,6 +741,28 @@ int rv_last_timings(float* out_ms, int cap) {
     return n;
 }
 int rv_last_launch_count(void) { return t_launches; }
+const char* rv_last_walker(void) { return t_walker; }
+void rv_set_jit_enabled(int enabled) { g_jit_override.store(enabled < 0 ? -1 : (enabled ? 1 : 0)); }
+
+int64_t rv_schema_walker_source(const rv_schema* s, char* buf, size_t cap) {
+    if (!s || !s->has_plan) return -1;
+    const std::string src = generate_walker_source(s->plan);
+    if (buf && cap) {
+        const size_t n = std::min(cap - 1, src.size());
+        std::memcpy(buf, src.data(), n);
+        buf[n] = 0;
+    }
+    return int64_t(src.size());
+}
+
+rv_status rv_schema_precompile(const rv_schema* s, const char* arch) {
+    rv_status st = check_decodable(s);
+    if (st) return st;
+    std::vector<char> cubin;
+    std::string log;
+    if (!jit_cubin(generate_kernel_source(s->plan), arch && *arch ? arch : "sm_100a", &cubin, &log)) return fail(RV_ERR_CUDA, "NVRTC: " + log);
+    return RV_OK;
+}
 const char* rv_last_error(void) { return t_error.c_str(); }
 const char* rv_version(void) { return "pyruhvro_b200 0.1.0 (sm_100a)"; }
 

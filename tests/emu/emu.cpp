@@ -18,7 +18,13 @@
 #include "../../pyruhvro_b200/csrc/plan.hpp"
 #include "../../pyruhvro_b200/csrc/result.hpp"
 #include "../../pyruhvro_b200/csrc/schema.hpp"
-#include "../../pyruhvro_b200/csrc/walker.cuh"
+#include "../../pyruhvro_b200/csrc/interp.cuh"
+#ifdef EMU_GEN_WALKER
+#include EMU_GEN_WALKER   // schema-specialised walker source produced by rv_schema_walker_source()
+using EmuWalker = rv::gen::Walker;
+#else
+using EmuWalker = rv::InterpWalker;
+#endif
 
 using namespace rv;
 
@@ -38,12 +44,13 @@ std::vector<Tile> make_tiles(int64_t n, int k) {
     return t;
 }
 
-void init_ctx(WalkCtx& c, const Plan& plan, const uint8_t* data, const int64_t* off, const Tile& t, int lane,
+using Ctx = WalkCtx<false>;
+
+void init_ctx(Ctx& c, const Plan& plan, const uint8_t* data, const int64_t* off, const Tile& t, int lane,
               uint32_t* cur, int S, void* const* bufs) {
     std::memset(&c, 0, sizeof c);
     c.nodes = plan.nodes.data();
     c.cur = cur + lane;
-    c.cur_stride = kTile;
     c.sym_off = plan.sym_off.data();
     c.sym_bytes = plan.sym_bytes.data();
     c.bufs = bufs;
@@ -83,9 +90,9 @@ int emu_decode(const char* json, size_t len, const uint8_t* data, const int64_t*
         for (size_t ti = 0; ti < tiles.size(); ++ti) {
             std::fill(cur.begin(), cur.end(), 0u);
             for (int lane = 0; lane < kTile; ++lane) {
-                WalkCtx c;
+                Ctx c;
                 init_ctx(c, plan, data, off, tiles[ti], lane, cur.data(), S, nullptr);
-                walk_record<WM_COUNT>(c, int(plan.nodes.size()));
+                EmuWalker::walk<WM_COUNT>(c, int(plan.nodes.size()));
                 if (c.in_range && c.err) { *err_record = tiles[ti].r0 + lane; return int(c.err); }
             }
             for (int s = 0; s < S; ++s) {
@@ -123,9 +130,9 @@ int emu_decode(const char* json, size_t len, const uint8_t* data, const int64_t*
             void* const* cb = bufs.data() + size_t(t.chunk) * size_t(n_slots);
             std::fill(cur.begin(), cur.end(), 0u);
             for (int lane = 0; lane < kTile; ++lane) {
-                WalkCtx c;
+                Ctx c;
                 init_ctx(c, plan, data, off, t, lane, cur.data(), S, nullptr);
-                walk_record<WM_COUNT>(c, int(plan.nodes.size()));
+                EmuWalker::walk<WM_COUNT>(c, int(plan.nodes.size()));
             }
             for (int s = 0; s < S; ++s) {  // exclusive scan across lanes + tile base
                 uint32_t run = tile_base[ti][size_t(s)];
@@ -135,9 +142,9 @@ int emu_decode(const char* json, size_t len, const uint8_t* data, const int64_t*
                 for (const DNode& nd : plan.nodes)
                     if (nd.kind == NK_STR || nd.kind == NK_ENUM || nd.kind == NK_LIST || nd.kind == NK_MAP) static_cast<int32_t*>(cb[nd.slot_a])[0] = 0;
             for (int lane = 0; lane < kTile; ++lane) {
-                WalkCtx c;
+                Ctx c;
                 init_ctx(c, plan, data, off, t, lane, cur.data(), S, cb);
-                walk_record<WM_EMIT>(c, int(plan.nodes.size()));
+                EmuWalker::walk<WM_EMIT>(c, int(plan.nodes.size()));
             }
         }
         // ---- null counts ----

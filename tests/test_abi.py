@@ -1,0 +1,139 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/ruhvro_b200.h declares; schema parse / gate / Arrow-schema export work without a GPU;
+the decode entry points fail loudly (never fall back) when no CUDA device is present."""
+import ctypes
+import json
+import os
+import random
+import re
+
+import pyarrow as pa
+import pytest
+
+import pyruhvro_b200 as pr
+from oracle import pyoracle as po
+from tests.golden import reference_datums as G
+from tests.parity import expected_schema
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_every_declared_symbol_is_exported():
+    header = open(os.path.join(ROOT, "include", "ruhvro_b200.h")).read()
+    names = set(re.findall(r"\b(rv_[a-z_0-9]+)\s*\(", header))
+    assert len(names) >= 20
+    lib = ctypes.CDLL(os.path.join(ROOT, "pyruhvro_b200", "libruhvro_b200.so"))
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+    lib.rv_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.rv_version()
+
+
+def test_python_surface_matches_reference_module():
+    import pyruhvro
+    for name in ("deserialize_array", "deserialize_array_threaded", "serialize_record_batch",
+                 "deserialize_array_threaded_spawn", "serialize_record_batch_spawn"):  # src/lib.rs:150-158
+        assert callable(getattr(pyruhvro, name))
+
+
+@pytest.mark.parametrize("seed", range(100))
+def test_arrow_schema_matches_schema_translate(seed):
+    sj = po.random_schema_json(random.Random(seed))
+    s = pr.Schema(sj)
+    assert s.is_supported
+    assert s.arrow_schema.equals(expected_schema(sj), check_metadata=True)
+
+
+def _walk_c_schema(addr):
+    s = pr._ArrowSchema.from_address(addr)
+    kids = []
+    if s.n_children:
+        arr = (ctypes.c_void_p * s.n_children).from_address(s.children)
+        kids = [_walk_c_schema(arr[i]) for i in range(s.n_children)]
+    return {"format": s.format.decode(), "name": (s.name or b"").decode(), "flags": s.flags, "children": kids}
+
+
+def test_c_level_map_and_union_field_names():
+    """pyarrow renames map children on import, so the names the reference produces
+    (schema_translate.rs:66-75: entries/keys/values) are checked on the raw C structs."""
+    sj = json.dumps({"type": "record", "name": "T", "fields": [
+        {"name": "m", "type": {"type": "map", "values": ["null", "long"]}},
+        {"name": "u", "type": ["null", "string", {"type": "enum", "name": "E", "namespace": "a.b", "symbols": ["X"]}]}]})
+    s = pr.Schema(sj)
+    cs = pr._ArrowSchema()
+    assert pr.lib.rv_schema_export_arrow(s.handle, ctypes.addressof(cs)) == 0
+    top = _walk_c_schema(ctypes.addressof(cs))
+    m, u = top["children"]
+    assert m["format"] == "+m" and m["flags"] == 0
+    entries = m["children"][0]
+    assert (entries["name"], entries["format"], entries["flags"]) == ("entries", "+s", 0)
+    assert [(c["name"], c["format"], c["flags"]) for c in entries["children"]] == [("keys", "u", 0), ("values", "l", 2)]
+    assert u["format"] == "+us:0,1,2" and u["flags"] == 2  # nullable because a null variant exists (:95-97)
+    assert [c["name"] for c in u["children"]] == ["null", "varchar", "a.b.E"]  # enum variant: fullname (:127-131)
+    pa.Schema._import_from_c(ctypes.addressof(cs))  # consumes/releases
+
+
+def test_metadata_doc_and_aliases():
+    sj = json.dumps({"type": "record", "name": "T", "namespace": "ns", "fields": [
+        {"name": "r", "type": {"type": "record", "name": "R", "doc": "rdoc", "aliases": ["Old", "x.Y"], "fields": [
+            {"name": "a", "type": "int", "doc": "adoc"}, {"name": "b", "type": "string"}]}},
+        {"name": "e", "doc": "ignored", "type": {"type": "enum", "name": "E", "doc": "edoc", "symbols": ["A"]}}]})
+    got = pr.Schema(sj).arrow_schema
+    assert got.equals(expected_schema(sj), check_metadata=True)
+    assert got.field("r").metadata == {b"avro::doc": b"rdoc", b"avro::aliases": b"[ns.Old,x.Y]"}
+    assert got.field("r").type.field("a").metadata == {b"avro::doc": b"adoc"}
+    assert got.field("e").metadata is None  # enum fields never carry metadata (schema_translate.rs:131)
+
+
+@pytest.mark.parametrize("bad", ["bytes", {"type": "fixed", "name": "F", "size": 4}, {"type": "string", "logicalType": "uuid"},
+                                 {"type": "int", "logicalType": "time-millis"}, {"type": "long", "logicalType": "time-micros"},
+                                 {"type": "bytes", "logicalType": "decimal", "precision": 4, "scale": 2}])
+def test_gate_rejects_what_the_reference_rejects(bad, coracle):
+    sj = json.dumps({"type": "record", "name": "T", "fields": [{"name": "x", "type": bad}, {"name": "y", "type": "int"}]})
+    assert not pr.Schema(sj).is_supported                 # fast_decode.rs:59
+    assert not coracle.is_supported(sj) and not po.is_supported(po.parse_schema(sj))
+
+
+def test_gate_rejects_named_refs_and_non_records(coracle):
+    sj = json.dumps({"type": "record", "name": "T", "fields": [
+        {"name": "a", "type": {"type": "record", "name": "A", "fields": [{"name": "x", "type": "int"}]}}, {"name": "b", "type": "A"}]})
+    assert not pr.Schema(sj).is_supported
+    assert not pr.Schema('"string"').is_supported
+    assert not pr.Schema('{"type":"array","items":"int"}').is_supported
+
+
+def test_unknown_logical_type_degrades_to_base():
+    sj = '{"type":"record","name":"T","fields":[{"name":"x","type":{"type":"long","logicalType":"made-up"}}]}'
+    s = pr.Schema(sj)
+    assert s.is_supported and s.arrow_schema.field("x").type == pa.int64()
+
+
+def test_schema_parse_errors_are_value_errors():
+    for bad in ["{", '{"type":"record","name":"T"}', '{"type":"record","name":"T","fields":[{"name":"x","type":["int","int"]}]}',
+                '{"type":"record","name":"T","fields":[{"name":"x","type":[["null","int"],"string"]}]}']:
+        with pytest.raises(ValueError):
+            pr.Schema(bad)
+
+
+def test_documented_limits_are_errors_not_crashes():
+    deep = "int"
+    for _ in range(5):
+        deep = {"type": "array", "items": deep}
+    sj = json.dumps({"type": "record", "name": "T", "fields": [{"name": "x", "type": deep}]})
+    s = pr.Schema(sj)
+    assert not s.is_supported  # array nesting > 3: no plan
+
+
+def test_decode_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(ValueError) as e:
+        pr.deserialize_array([bytes.fromhex(G.G2_HEX)], G.G2_SCHEMA)
+    assert "CUDA" in str(e.value) or "pinned" in str(e.value)
+    with pytest.raises(ValueError):
+        import numpy as np
+        data, off = po.pack_records([bytes.fromhex(G.G2_HEX)])
+        pr.decode_packed(data, off, 1, G.G2_SCHEMA, 1)
+    with pytest.raises(NotImplementedError):
+        pr.serialize_record_batch(None, G.G2_SCHEMA, 1)

@@ -27,6 +27,30 @@ def test_random_schemas(coracle, seed):
     assert_matches_oracle(coracle, emu.decode(sj, data, off, len(recs), k), sj, data, off, len(recs), k)
 
 
+@pytest.mark.parametrize("seed", range(100, 124))
+def test_generated_walker_random_schemas(coracle, seed):
+    """The schema-specialised walker source that NVRTC compiles for the GPU, compiled for the host."""
+    sj, recs, data, off = gen_case(seed)
+    k = random.Random(seed).choice([1, 2, 5])
+    assert_matches_oracle(coracle, emu.decode(sj, data, off, len(recs), k, walker="gen"), sj, data, off, len(recs), k)
+
+
+def test_generated_walker_goldens_and_errors(coracle):
+    from tests import malformed as M
+    for sj, recs in [(G.G1_SCHEMA, [bytes.fromhex(G.G1_HEX)] * 4), (G.G2_SCHEMA, [bytes.fromhex(G.G2_HEX)]),
+                     (G.G345_SCHEMA, [bytes.fromhex(h) for h in (G.G3_HEX, G.G4_HEX, G.G5_HEX)])]:
+        data, off = po.pack_records(recs)
+        assert_matches_oracle(coracle, emu.decode(sj, data, off, len(recs), 2, walker="gen"), sj, data, off, len(recs), 2)
+    good = [M.good_record(i) for i in range(300)]
+    for name, code, bad in M.cases():
+        recs = list(good)
+        recs[37] = bad
+        data, off = po.pack_records(recs)
+        with pytest.raises(emu.EmuError) as ee:
+            emu.decode(M.FLAT, data, off, len(recs), 3, walker="gen")
+        assert (po.ERR_NAMES[ee.value.code], ee.value.record) == (code, 37), name
+
+
 def test_empty_input(coracle):
     sj = G.G345_SCHEMA
     data, off = po.pack_records([])

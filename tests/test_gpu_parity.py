@@ -12,8 +12,19 @@ from tests.parity import assert_matches_oracle, gen_case
 
 pytestmark = pytest.mark.gpu
 
+JIT_SEEDS = list(range(40))       # schemas whose specialised kernels tools/warm_jit_cache.py precompiles
+INTERP_SEEDS = list(range(80))
 
-def test_goldens_values_and_buffers(coracle):
+
+@pytest.fixture(params=["jit", "interp"])
+def walker(request):
+    """Runs the test once per GPU walker: NVRTC-specialised kernels and the generic interpreter kernels."""
+    pr.set_jit_enabled(1 if request.param == "jit" else 0)
+    yield request.param
+    pr.set_jit_enabled(-1)
+
+
+def test_goldens_values_and_buffers(coracle, walker):
     recs = [bytes.fromhex(h) for h in (G.G3_HEX, G.G4_HEX, G.G5_HEX)]
     b = pr.deserialize_array(recs, G.G345_SCHEMA)
     rows = b.to_pylist()
@@ -30,10 +41,10 @@ def test_goldens_values_and_buffers(coracle):
     assert g1.column("age").to_pylist() == [28] * 4
     g2 = pr.deserialize_array([bytes.fromhex(G.G2_HEX)], G.G2_SCHEMA)
     assert g2.to_pylist() == [G.G2_ROW]                    # deserialize.rs:307-308 (+ values)
+    assert pr.last_walker() == walker
 
 
-@pytest.mark.parametrize("seed", range(80))
-def test_random_schemas(coracle, seed):
+def _random_case(coracle, seed):
     rng = random.Random(1000 + seed)
     n = rng.choice([1, 31, 32, 33, 255, 256, 257, 600, 2500])
     sj, recs, data, off = gen_case(seed, n=n)
@@ -41,7 +52,27 @@ def test_random_schemas(coracle, seed):
     assert_matches_oracle(coracle, pr.deserialize_array_threaded(recs, sj, k), sj, data, off, n, k)
 
 
-def test_packed_c_abi_path(coracle):
+@pytest.mark.parametrize("seed", JIT_SEEDS)
+def test_random_schemas_jit(coracle, seed):
+    pr.set_jit_enabled(1)
+    try:
+        _random_case(coracle, seed)
+        assert pr.last_walker() == "jit"
+    finally:
+        pr.set_jit_enabled(-1)
+
+
+@pytest.mark.parametrize("seed", INTERP_SEEDS)
+def test_random_schemas_interp(coracle, seed):
+    pr.set_jit_enabled(0)
+    try:
+        _random_case(coracle, seed)
+        assert pr.last_walker() == "interp"
+    finally:
+        pr.set_jit_enabled(-1)
+
+
+def test_packed_c_abi_path(coracle, walker):
     sj, recs, data, off = gen_case(7, n=5000)
     assert_matches_oracle(coracle, pr.decode_packed(data, off, len(recs), sj, 8), sj, data, off, len(recs), 8)
 
@@ -58,7 +89,7 @@ def test_empty_and_partition(coracle):
         assert_matches_oracle(coracle, b, sj, data, off, n, k)
 
 
-def test_malformed_inputs(coracle):
+def test_malformed_inputs(coracle, walker):
     from tests import malformed as M
     good = [M.good_record(i) for i in range(700)]
     for name, code, bad in M.cases():
@@ -76,6 +107,14 @@ def test_malformed_inputs(coracle):
     assert_matches_oracle(coracle, pr.deserialize_array_threaded(recs, M.FLAT, 2), M.FLAT, data, off, len(recs), 2)
 
 
+def test_benchmark_workloads_small(coracle, walker):
+    import workloads
+    for name in ("flat", "kafka", "wide", "array_map", "nested", "nullable"):
+        sj, data, off = workloads.generate(name, 30000, seed=7)
+        assert_matches_oracle(coracle, pr.decode_packed(data, off, 30000, sj, 8), sj, data, off, 30000, 8, full_validate=False)
+        assert pr.last_walker() == walker
+
+
 def test_error_surface():
     with pytest.raises(TypeError):
         pr.deserialize_array([b"ok", "not-bytes"], G.G1_SCHEMA)
@@ -85,8 +124,9 @@ def test_error_surface():
         pr.deserialize_array([b""], "{not json")
 
 
-def test_large_records_use_global_path(coracle):
-    """Records far larger than the shared-memory tile exercise the direct-from-global walk."""
+def test_large_records_use_global_path(coracle, walker):
+    """Records far larger than the shared-memory tile exercise the direct-from-global walk; under the
+    specialised kernels those tiles are routed to the interpreter kernels through the overflow list."""
     sj = '{"type":"record","name":"L","fields":[{"name":"s","type":"string"},{"name":"a","type":{"type":"array","items":"long"}}]}'
     s = po.parse_schema(sj)
     rng = random.Random(9)
@@ -95,7 +135,7 @@ def test_large_records_use_global_path(coracle):
     assert_matches_oracle(coracle, pr.deserialize_array_threaded(recs, sj, 2), sj, data, off, len(recs), 2)
 
 
-def test_zero_width_items_and_deep_nesting(coracle):
+def test_zero_width_items_and_deep_nesting(coracle, walker):
     sj = '{"type":"record","name":"Z","fields":[{"name":"z","type":{"type":"array","items":"null"}},' \
          '{"name":"m","type":{"type":"map","values":{"type":"array","items":{"type":"array","items":["null","string"]}}}}]}'
     s = po.parse_schema(sj)
