@@ -209,8 +209,32 @@ template <class C>
 RV_HD void copy_from_record(C& c, int slot_b, int stream, uint32_t o, uint32_t s, uint32_t len) {
 #if defined(__CUDA_ARCH__)
     if (c.stage_on) {
-        const uint32_t d = c.stage_soff + c.stage_adj[stream] + o;
-        for (uint32_t i = 0; i < len; ++i) rv_smem[d + i] = uint8_t(ld_u8(c, s + i));
+        uint32_t d = c.stage_soff + c.stage_adj[stream] + o;
+        if (C::kShared) {
+            // shared -> shared, word at a time: the warp's cost is its LONGEST string, so iterations matter.
+            // Head bytes bring the destination to a 4-byte boundary; interior words are assembled from two
+            // aligned source words with a funnel shift; tail bytes finish.  Reading the source word past the
+            // string's end stays inside the staged tile window (16-byte padded).
+            uint32_t sa = c.soff + s;
+            uint32_t n = len;
+            while (n && (d & 3u)) { rv_smem[d++] = rv_smem[sa++]; --n; }
+            if (n >= 4u) {
+                const uint32_t sh = (sa & 3u) * 8u;
+                const uint32_t* sw = reinterpret_cast<const uint32_t*>(rv_smem + (sa & ~3u));
+                uint32_t* dw = reinterpret_cast<uint32_t*>(rv_smem + d);
+                const uint32_t nw = n >> 2;
+                uint32_t lo = sw[0];
+                for (uint32_t j = 0; j < nw; ++j) {
+                    const uint32_t hi = sw[j + 1];
+                    dw[j] = __funnelshift_r(lo, hi, sh);
+                    lo = hi;
+                }
+                d += nw << 2; sa += nw << 2; n &= 3u;
+            }
+            while (n) { rv_smem[d++] = rv_smem[sa++]; --n; }
+        } else {
+            for (uint32_t i = 0; i < len; ++i) rv_smem[d + i] = uint8_t(ld_u8(c, s + i));
+        }
         return;
     }
 #endif

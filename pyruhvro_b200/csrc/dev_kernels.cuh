@@ -10,7 +10,7 @@
 //               values / offsets are stored row-aligned; space-0 validity is one ballot word per warp.
 //
 // Shared-memory map (dynamic, rv_smem):
-//   [nodes n_nodes*32][cur S*256*4][wtot S*8*4][tot (S+1)*4][adj S*4][in: smem_data_cap][out: smem_stage_cap]
+//   [nodes n_nodes*32][cur S*256*4][wtot S*8*4 (emit: tile bases)][tot (S+1)*4][adj S*4][in: smem_data_cap][out: smem_stage_cap]
 #pragma once
 #include "dev_core.cuh"
 
@@ -133,34 +133,10 @@ __device__ __forceinline__ void count_body(const DecodeParams& p, const int tile
         return;  // uniform: the whole CTA leaves
     }
     __syncthreads();
-    const uint32_t* cur = reinterpret_cast<const uint32_t*>(rv_smem + m.cur);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int s = warp; s < p.n_streams; s += kWarps) {
-        unsigned long long sum = 0;
-        for (int i = lane; i < kBlock; i += 32) sum += cur[s * kBlock + i];
-        for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
-        if (lane == 0) {
-            if (sum > 0x7FFFFFFFull) { report(p, t.r0, E_OVERFLOW); sum = 0x7FFFFFFFull; }
-            p.tile_agg[size_t(s) * p.n_tiles + tile_id] = uint32_t(sum);
-        }
-    }
-}
-
-// ---- emit -----------------------------------------------------------------------------------
-template <class W, bool SM>
-__device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t, const int tile_id, const SmemMap& m, const TileWindow& w) {
-    WalkCtx<SM> c;
-    (void)init_ctx(c, p, t, m, w);
-    const uint32_t pos0 = c.pos;
-    W::template walk<WM_COUNT>(c, p.n_nodes);
-    const uint32_t count_err = c.err;
-    __syncthreads();
-
-    // CTA-wide exclusive scan of every stream's lane counts.
+    // CTA-wide exclusive scan of every stream's lane counts.  The per-record prefixes are saved so the
+    // emit kernel does not have to walk the records a second time just to learn where they write.
     uint32_t* cur = reinterpret_cast<uint32_t*>(rv_smem + m.cur);
     uint32_t* wtot = reinterpret_cast<uint32_t*>(rv_smem + m.wtot);
-    uint32_t* tot = reinterpret_cast<uint32_t*>(rv_smem + m.tot);
-    uint32_t* adj = reinterpret_cast<uint32_t*>(rv_smem + m.adj);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int s = 0; s < p.n_streams; ++s) {
         const uint32_t v = cur[s * kBlock + tid];
@@ -173,37 +149,65 @@ __device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t,
         cur[s * kBlock + tid] = incl - v;
     }
     __syncthreads();
-    // Tile totals and the staging map of the Utf8 streams.  Stream s's bytes of this tile occupy
-    // [tile_base, tile_base + tot) of its Arrow data buffer; in shared memory its region starts at an
-    // offset congruent (mod 16) to the global destination so the write-out can use aligned uint4.
+    // one thread per stream: exclusive prefix of the warp totals (in place) + the tile total
+    if (tid < p.n_streams) {
+        unsigned long long run = 0;
+        for (int ww = 0; ww < kWarps; ++ww) {
+            const uint32_t v = wtot[tid * kWarps + ww];
+            wtot[tid * kWarps + ww] = uint32_t(run);
+            run += v;
+        }
+        if (run > 0x7FFFFFFFull) { report(p, t.r0, E_OVERFLOW); run = 0x7FFFFFFFull; }
+        p.tile_agg[size_t(tid) * p.n_tiles + tile_id] = uint32_t(run);
+    }
+    __syncthreads();
+    uint32_t* lo = p.lane_off + size_t(tile_id) * p.n_streams * kBlock;
+    for (int s = 0; s < p.n_streams; ++s) lo[s * kBlock + tid] = cur[s * kBlock + tid] + wtot[s * kWarps + warp];
+}
+
+// ---- emit -----------------------------------------------------------------------------------
+template <class W, bool SM>
+__device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t, const int tile_id, const SmemMap& m, const TileWindow& w) {
+    WalkCtx<SM> c;
+    (void)init_ctx(c, p, t, m, w);
+    uint32_t* cur = reinterpret_cast<uint32_t*>(rv_smem + m.cur);
+    uint32_t* tbase = reinterpret_cast<uint32_t*>(rv_smem + m.wtot);  // reused: [S] tile bases, then [S] region alignments
+    uint32_t* tot = reinterpret_cast<uint32_t*>(rv_smem + m.tot);
+    uint32_t* adj = reinterpret_cast<uint32_t*>(rv_smem + m.adj);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // Each record's first row / first byte per stream = the chunk-relative tile base (scan_kernel) + the
+    // record's prefix inside the tile (count kernel).
+    const uint32_t* lo = p.lane_off + size_t(tile_id) * p.n_streams * kBlock;
+    for (int s = 0; s < p.n_streams; ++s)
+        cur[s * kBlock + tid] = __ldg(lo + s * kBlock + tid) + __ldg(p.tile_base + size_t(s) * p.n_tiles + tile_id);
+    if (tid < p.n_streams) {
+        const uint32_t tb = __ldg(p.tile_base + size_t(tid) * p.n_tiles + tile_id);
+        tbase[tid] = tb;
+        tot[tid] = __ldg(p.tile_agg + size_t(tid) * p.n_tiles + tile_id);
+        const int slot = p.stream_slot[tid];
+        tbase[p.n_streams + tid] = slot >= 0 ? uint32_t(reinterpret_cast<uintptr_t>(static_cast<uint8_t*>(c.bufs[slot]) + tb) & 15u) : 0u;
+    }
+    __syncthreads();
+    // Staging map of the Utf8 streams.  Stream s's bytes of this tile occupy [tile_base, tile_base + tot)
+    // of its Arrow data buffer; in shared memory its region starts at an offset congruent (mod 16) to the
+    // global destination so the write-out can use aligned uint4.
     if (tid == 0) {
         uint32_t off = 0;
         bool fits = p.smem_stage_cap > 0;
         for (int s = 0; s < p.n_streams; ++s) {
-            uint32_t tt = 0;
-            for (int ww = 0; ww < kWarps; ++ww) tt += wtot[s * kWarps + ww];
-            tot[s] = tt;
-            const int slot = p.stream_slot[s];
-            if (slot >= 0) {
-                const uint32_t tb = p.tile_base[size_t(s) * p.n_tiles + tile_id];
-                const uint32_t galign = uint32_t(reinterpret_cast<uintptr_t>(static_cast<uint8_t*>(c.bufs[slot]) + tb) & 15u);
-                const uint32_t start = ((off + 15u) & ~15u) + galign;
-                adj[s] = start - tb;  // staging offset of byte `o` (chunk-relative) = adj + o
-                off = start + tt;
+            if (p.stream_slot[s] >= 0) {
+                const uint32_t start = ((off + 15u) & ~15u) + tbase[p.n_streams + s];
+                adj[s] = start - tbase[s];  // staging offset of chunk-relative byte `o` = adj + o
+                off = start + tot[s];
                 if (off > p.smem_stage_cap) fits = false;
             } else {
                 adj[s] = 0;
             }
         }
-        tot[p.n_streams] = fits ? 1u : 0u;  // tot has S+1 entries
+        tot[p.n_streams] = fits ? 1u : 0u;
     }
     __syncthreads();
     const bool stage_on = p.n_streams > 0 && tot[p.n_streams] != 0;
-    for (int s = 0; s < p.n_streams; ++s) {
-        uint32_t b = __ldg(p.tile_base + size_t(s) * p.n_tiles + tile_id);
-        for (int ww = 0; ww < warp; ++ww) b += wtot[s * kWarps + ww];
-        cur[s * kBlock + tid] += b;
-    }
     // offsets[0] = 0 of every offsets buffer of this chunk (first tile of the chunk only)
     if (t.local_tile == 0) {
         if (p.n_nodes) {
@@ -216,8 +220,6 @@ __device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t,
             W::zero_offsets(c, tid);
         }
     }
-    c.pos = pos0;
-    c.err = count_err;  // a record that failed validation emits only null slots
     c.stage_on = stage_on;
     W::template walk<WM_EMIT>(c, p.n_nodes);
 
@@ -227,7 +229,7 @@ __device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t,
             const int slot = p.stream_slot[s];
             const uint32_t n = tot[s];
             if (slot < 0 || n == 0) continue;
-            const uint32_t tb = __ldg(p.tile_base + size_t(s) * p.n_tiles + tile_id);
+            const uint32_t tb = tbase[s];
             uint8_t* g = static_cast<uint8_t*>(c.bufs[slot]) + tb;
             const uint32_t so = m.out + adj[s] + tb;  // rv_smem offset of the region's first byte
             const uint32_t head = min(n, (16u - uint32_t(reinterpret_cast<uintptr_t>(g) & 15u)) & 15u);

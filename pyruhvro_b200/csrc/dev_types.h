@@ -106,6 +106,7 @@ struct DecodeParams {
     // scan scratch
     uint32_t* tile_agg;    // [n_streams][n_tiles] per-tile totals
     uint32_t* tile_base;   // [n_streams][n_tiles] exclusive prefix within the chunk
+    uint32_t* lane_off;    // [n_tiles][n_streams][kBlock] each record's exclusive prefix inside its tile
     unsigned long long* chunk_tot;  // [k][n_streams]
     unsigned long long* err;        // min over (record << 8 | code); ~0 = none
     // output

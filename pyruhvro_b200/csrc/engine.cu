@@ -324,13 +324,13 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
 
     std::vector<unsigned long long> chunk_tot(size_t(k) * size_t(std::max(S, 1)), 0ull);
     DecodeParams p{};
-    DevBuf tile_agg, tile_base, d_chunk_tot, d_err, d_bufs, d_overflow;
+    DevBuf tile_agg, tile_base, lane_off, d_chunk_tot, d_err, d_bufs, d_overflow;
     DecodeParams pi{};   // interpreter pass over the tiles the specialised kernels skipped
     size_t smem_interp = 0;
     cudaEvent_t ev[8];
     for (auto& e : ev) RV_CUDA(cudaEventCreate(&e));
     struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 8; ++i) cudaEventDestroy(e[i]); } } evg{ev};
-    size_t smem_count = 0, smem_emit = 0;
+    size_t smem_count = 0, smem_emit = 0, smem_room_out = 0;
     bool use_jit = false;
     cudaKernel_t jit_count = nullptr, jit_emit = nullptr;
 
@@ -364,19 +364,15 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         const size_t limit = 227 * 1024;
         if (fixed + 2048 > limit) return fail(RV_ERR_SCHEMA, "schema too wide for the shared-memory cursor table");
         const double avg = total_bytes > 0 ? double(total_bytes) / double(n) : 16.0;
-        size_t want = size_t(avg * kBlock * 1.25) + 1024;
-        want = (want + 1023) & ~size_t(1023);
+        // a tile is the sum of 256 record sizes: its spread is a few percent, so a 12% margin keeps almost
+        // every tile in shared memory while letting three CTAs share an SM on the Kafka-shaped workloads
+        size_t want = size_t(avg * kBlock * 1.12) + 768;
+        want = (want + 255) & ~size_t(255);
         want = std::max<size_t>(want, 4096);
         const size_t room = (limit - fixed - 64) & ~size_t(15);
         size_t cap_in = std::min(want, room);
-        size_t cap_out = 0;
-        bool any_bytes = false;
-        for (const Stream& st_ : plan.streams) any_bytes |= !st_.is_rows;
-        if (any_bytes && room > cap_in + 1024) cap_out = std::min(want + 256, (room - cap_in) & ~size_t(15));
-        if (const char* e = std::getenv("RV_NO_STAGE_OUT")) if (e[0] == '1') cap_out = 0;
         smem_count = smem_map(plan_nodes, S, uint32_t(cap_in)).out;
-        smem_emit = smem_count + cap_out;
-        p.smem_stage_cap = uint32_t(cap_out);
+        smem_room_out = room > cap_in ? room - cap_in : 0;
         p.stream_slot = dp.stream_slot;
         const int n_nodes_param = plan_nodes;
         p.data = d_data; p.offsets = d_offsets; p.n = n; p.chunk_rows = chunk_rows; p.k = k;
@@ -386,12 +382,14 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         p.smem_data_cap = uint32_t(cap_in);
         RV_CUDA(tile_agg.alloc(size_t(std::max(S, 1)) * size_t(n_tiles) * 4, stream));
         RV_CUDA(tile_base.alloc(size_t(std::max(S, 1)) * size_t(n_tiles) * 4, stream));
+        RV_CUDA(lane_off.alloc(size_t(std::max(S, 1)) * size_t(n_tiles) * kBlock * 4, stream));
         RV_CUDA(d_chunk_tot.alloc(chunk_tot.size() * 8, stream));
         RV_CUDA(d_err.alloc(8, stream));
         RV_CUDA(d_overflow.alloc((size_t(n_tiles) + 1) * 4, stream));
         RV_CUDA(cudaMemsetAsync(d_overflow.p, 0, 4, stream));
         p.tile_agg = static_cast<uint32_t*>(tile_agg.p);
         p.tile_base = static_cast<uint32_t*>(tile_base.p);
+        p.lane_off = static_cast<uint32_t*>(lane_off.p);
         p.chunk_tot = static_cast<unsigned long long*>(d_chunk_tot.p);
         p.err = static_cast<unsigned long long*>(d_err.p);
         p.bufs = nullptr;
@@ -448,6 +446,27 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         RV_CUDA(cudaMemcpyAsync(d_bufs.p, h_bufs.data(), h_bufs.size() * sizeof(void*), cudaMemcpyHostToDevice, stream));
         p.bufs = static_cast<void* const*>(d_bufs.p);
 
+        // Utf8 staging area of the emit CTAs, sized from the now-known string totals: a tile's share of
+        // every Utf8 column (+12%) plus 16 bytes of alignment slack per column.
+        {
+            unsigned long long utf8 = 0;
+            int n_utf8 = 0;
+            for (int st_ = 0; st_ < S; ++st_) {
+                if (plan.streams[size_t(st_)].is_rows) continue;
+                ++n_utf8;
+                for (int j = 0; j < k; ++j) utf8 += chunk_tot[size_t(j) * size_t(S) + size_t(st_)];
+            }
+            size_t cap_out = 0;
+            if (n_utf8 > 0) {
+                cap_out = size_t(double(utf8) / double(p.n_tiles) * 1.12) + size_t(n_utf8) * 32 + 512;
+                cap_out = (cap_out + 255) & ~size_t(255);
+                if (cap_out > smem_room_out) cap_out = smem_room_out & ~size_t(15);
+                if (cap_out < 1024) cap_out = 0;
+            }
+            if (const char* ev_ = std::getenv("RV_NO_STAGE_OUT")) if (ev_[0] == '1') cap_out = 0;
+            p.smem_stage_cap = uint32_t(cap_out);
+            smem_emit = smem_count + cap_out;
+        }
         RV_CUDA(cudaEventRecord(ev[3], stream));
         if (use_jit) {
             void* args[] = {&p};
