@@ -50,9 +50,12 @@ struct WalkCtx {
     bool store_word;       // space-0 bitmaps: this lane stores the warp's ballot word
 };
 
+// Records the first error of the record and parks the cursor at the record's end, so every later
+// read of this lane fails on its own (EOF) without the walkers re-checking c.err at each node.
 template <class C>
 RV_HD void fail(C& c, uint32_t code) {
     if (!c.err) c.err = code;
+    c.pos = c.end;
 }
 
 template <class C>
@@ -86,6 +89,30 @@ RV_HD int64_t rd_varint(C& c) {
         if (shift >= 64) { fail(c, E_VARINT); return 0; }
     }
     return zz64(r);
+}
+
+// Length prefix of a string (read_string, fast_decode.rs:902-911): false on error.
+template <class C>
+RV_HD bool rd_len(C& c, uint32_t& len) {
+    bool have = false;
+    if (c.pos < c.end) {
+        const uint32_t b = ld_u8(c, c.pos);
+        if (b < 0x80u) {  // one byte: zigzag(len) < 128, odd = negative
+            c.pos += 1;
+            if (b & 1u) { fail(c, E_NEG_LEN); return false; }
+            len = b >> 1;
+            have = true;
+        }
+    }
+    if (!have) {
+        const int64_t l = rd_varint(c);
+        if (c.err) return false;
+        if (l < 0) { fail(c, E_NEG_LEN); return false; }
+        if (l > int64_t(0xFFFFFFFFu)) { fail(c, E_EOF); return false; }
+        len = uint32_t(l);
+    }
+    if (len > c.end - c.pos) { fail(c, E_EOF); return false; }
+    return true;
 }
 
 // union_branch (fast_decode.rs:585-593): true = Value, false = Null (or error).
@@ -209,29 +236,38 @@ template <class C>
 RV_HD void copy_from_record(C& c, int slot_b, int stream, uint32_t o, uint32_t s, uint32_t len) {
 #if defined(__CUDA_ARCH__)
     if (c.stage_on) {
-        uint32_t d = c.stage_soff + c.stage_adj[stream] + o;
+        const uint32_t d = c.stage_soff + c.stage_adj[stream] + o;
         if (C::kShared) {
-            // shared -> shared, word at a time: the warp's cost is its LONGEST string, so iterations matter.
-            // Head bytes bring the destination to a 4-byte boundary; interior words are assembled from two
-            // aligned source words with a funnel shift; tail bytes finish.  Reading the source word past the
-            // string's end stays inside the staged tile window (16-byte padded).
-            uint32_t sa = c.soff + s;
-            uint32_t n = len;
-            while (n && (d & 3u)) { rv_smem[d++] = rv_smem[sa++]; --n; }
-            if (n >= 4u) {
-                const uint32_t sh = (sa & 3u) * 8u;
-                const uint32_t* sw = reinterpret_cast<const uint32_t*>(rv_smem + (sa & ~3u));
-                uint32_t* dw = reinterpret_cast<uint32_t*>(rv_smem + d);
-                const uint32_t nw = n >> 2;
-                uint32_t lo = sw[0];
-                for (uint32_t j = 0; j < nw; ++j) {
-                    const uint32_t hi = sw[j + 1];
-                    dw[j] = __funnelshift_r(lo, hi, sh);
+            // shared -> shared, one destination WORD per iteration (the warp's cost is its longest string,
+            // so iterations matter).  Destination word j takes 4 source bytes at an arbitrary alignment:
+            // two aligned source words + a funnel shift.  The first and last words are shared with the
+            // neighbouring strings (written by other lanes), so they are merged with atomicOr into the
+            // zero-initialised staging area; interior words are plain stores.  Source reads may touch up to
+            // 3 bytes before / 4 bytes after the string: still inside the CTA's shared memory.
+            const uint32_t a = d & 3u;
+            const uint32_t nwords = (a + len + 3u) >> 2;
+            const uint32_t sp = c.soff + s - a;  // source byte that lands in byte 0 of destination word 0
+            const uint32_t sh = (sp & 3u) * 8u;
+            const uint32_t* sw = reinterpret_cast<const uint32_t*>(rv_smem + (sp & ~3u));
+            uint32_t* dw = reinterpret_cast<uint32_t*>(rv_smem + (d & ~3u));
+            const uint32_t m_first = 0xFFFFFFFFu << (a * 8u);
+            const uint32_t e = (a + len) & 3u;
+            const uint32_t m_last = e ? (0xFFFFFFFFu >> ((4u - e) * 8u)) : 0xFFFFFFFFu;
+            uint32_t lo = sw[0], hi = sw[1];
+            uint32_t v = __funnelshift_r(lo, hi, sh);
+            if (nwords == 1u) {
+                atomicOr(dw, v & m_first & m_last);
+            } else {
+                atomicOr(dw, v & m_first);
+                for (uint32_t j = 1; j + 1 < nwords; ++j) {
                     lo = hi;
+                    hi = sw[j + 1];
+                    dw[j] = __funnelshift_r(lo, hi, sh);
                 }
-                d += nw << 2; sa += nw << 2; n &= 3u;
+                lo = hi;
+                hi = sw[nwords];
+                atomicOr(dw + (nwords - 1u), __funnelshift_r(lo, hi, sh) & m_last);
             }
-            while (n) { rv_smem[d++] = rv_smem[sa++]; --n; }
         } else {
             for (uint32_t i = 0; i < len; ++i) rv_smem[d + i] = uint8_t(ld_u8(c, s + i));
         }
@@ -276,13 +312,9 @@ template <int MODE, int D, class C>
 RV_HD void op_str(C& c, bool valid, int slot_a, int slot_b, int slot_v, int stream, uint32_t row) {  // read_string :902-922
     uint32_t len = 0;
     if (valid) {
-        const int64_t l = rd_varint(c);
-        if (c.err) valid = false;
-        else if (l < 0) { fail(c, E_NEG_LEN); valid = false; }
-        else if (uint64_t(l) > uint64_t(c.end - c.pos)) { fail(c, E_EOF); valid = false; }
+        if (!rd_len(c, len)) { valid = false; len = 0; }
         else {
-            len = uint32_t(l);
-            if (MODE == WM_EMIT) copy_from_record(c, slot_b, stream, c.cur[uint32_t(stream) * kBlock], c.pos, len);
+            if (MODE == WM_EMIT && len) copy_from_record(c, slot_b, stream, c.cur[uint32_t(stream) * kBlock], c.pos, len);
             c.pos += len;
         }
     }

@@ -26,8 +26,11 @@ struct Tile {
 
 __device__ __forceinline__ Tile tile_of(const DecodeParams& p, int tile) {
     Tile t;
-    int j = tile / p.tiles_per_chunk;
-    if (j > p.k - 1) j = p.k - 1;
+    int j = 0;
+    if (p.k > 1) {
+        j = tile / p.tiles_per_chunk;
+        if (j > p.k - 1) j = p.k - 1;
+    }
     t.chunk = j;
     t.local_tile = tile - j * p.tiles_per_chunk;
     const int64_t cs = int64_t(j) * p.chunk_rows;
@@ -46,14 +49,25 @@ struct TileWindow {
 };
 
 // Loads the plan and the tile's byte window into shared memory.
-__device__ __forceinline__ TileWindow stage_in(const DecodeParams& p, const Tile& t, const SmemMap& m) {
+// EMIT: the lanes' cursors (tile base + in-tile prefix) and, further down, zeroing of the Utf8 staging
+// area are issued here too, so their latency overlaps the input loads.
+template <bool EMIT>
+__device__ __forceinline__ TileWindow stage_in(const DecodeParams& p, const Tile& t, const int tile_id, const SmemMap& m) {
     const int tid = threadIdx.x;
     if (p.n_nodes) {
         uint4* dn = reinterpret_cast<uint4*>(rv_smem + m.nodes);
         for (int i = tid; i < p.n_nodes * 2; i += kBlock) dn[i] = __ldg(reinterpret_cast<const uint4*>(p.nodes) + i);
     }
     uint32_t* cur = reinterpret_cast<uint32_t*>(rv_smem + m.cur);
-    for (int s = 0; s < p.n_streams; ++s) cur[s * kBlock + tid] = 0;
+    if (EMIT) {
+        const uint32_t* lo = p.lane_off + size_t(tile_id) * p.n_streams * kBlock;
+        for (int s = 0; s < p.n_streams; ++s)
+            cur[s * kBlock + tid] = __ldg(lo + s * kBlock + tid) + __ldg(p.tile_base + size_t(s) * p.n_tiles + tile_id);
+        uint4* z = reinterpret_cast<uint4*>(rv_smem + m.out);
+        for (uint32_t i = tid; i < (p.smem_stage_cap >> 4); i += kBlock) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+        for (int s = 0; s < p.n_streams; ++s) cur[s * kBlock + tid] = 0;
+    }
     TileWindow w;
     w.t0 = __ldg(p.offsets + t.r0);
     w.t1 = __ldg(p.offsets + t.r0 + t.nrec);
@@ -124,7 +138,7 @@ template <class W, bool GENERIC>
 __device__ __forceinline__ void count_body(const DecodeParams& p, const int tile_id) {
     const Tile t = tile_of(p, tile_id);
     const SmemMap m = smem_map(p.n_nodes, p.n_streams, p.smem_data_cap);
-    const TileWindow w = stage_in(p, t, m);
+    const TileWindow w = stage_in<false>(p, t, tile_id, m);
     __syncthreads();
     if (w.staged) count_walk<W, true>(p, t, m, w);
     else if constexpr (GENERIC) count_walk<W, false>(p, t, m, w);
@@ -170,16 +184,12 @@ template <class W, bool SM>
 __device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t, const int tile_id, const SmemMap& m, const TileWindow& w) {
     WalkCtx<SM> c;
     (void)init_ctx(c, p, t, m, w);
-    uint32_t* cur = reinterpret_cast<uint32_t*>(rv_smem + m.cur);
     uint32_t* tbase = reinterpret_cast<uint32_t*>(rv_smem + m.wtot);  // reused: [S] tile bases, then [S] region alignments
     uint32_t* tot = reinterpret_cast<uint32_t*>(rv_smem + m.tot);
     uint32_t* adj = reinterpret_cast<uint32_t*>(rv_smem + m.adj);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // Each record's first row / first byte per stream = the chunk-relative tile base (scan_kernel) + the
-    // record's prefix inside the tile (count kernel).
-    const uint32_t* lo = p.lane_off + size_t(tile_id) * p.n_streams * kBlock;
-    for (int s = 0; s < p.n_streams; ++s)
-        cur[s * kBlock + tid] = __ldg(lo + s * kBlock + tid) + __ldg(p.tile_base + size_t(s) * p.n_tiles + tile_id);
+    // (each record's first row / first byte per stream was loaded into `cur` by stage_in: the chunk-relative
+    // tile base from scan_kernel + the record's prefix inside the tile from the count kernel)
     if (tid < p.n_streams) {
         const uint32_t tb = __ldg(p.tile_base + size_t(tid) * p.n_tiles + tile_id);
         tbase[tid] = tb;
@@ -248,7 +258,7 @@ template <class W, bool GENERIC>
 __device__ __forceinline__ void emit_body(const DecodeParams& p, const int tile_id) {
     const Tile t = tile_of(p, tile_id);
     const SmemMap m = smem_map(p.n_nodes, p.n_streams, p.smem_data_cap);
-    const TileWindow w = stage_in(p, t, m);
+    const TileWindow w = stage_in<true>(p, t, tile_id, m);
     __syncthreads();
     if (w.staged) emit_walks<W, true>(p, t, tile_id, m, w);
     else if constexpr (GENERIC) emit_walks<W, false>(p, t, tile_id, m, w);
