@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="kafka", choices=list(WORKLOAD_DESC))
     ap.add_argument("--records", type=int, default=10_000_000, help="records per GPU")
-    ap.add_argument("--num-chunks", type=int, default=1)
+    ap.add_argument("--num-chunks", type=int, default=8, help="output batches per call (README bench: 8)")
     ap.add_argument("--cpu-sample", type=int, default=4_000_000)
     ap.add_argument("--seed", type=int, default=42)
     return ap.parse_args()

@@ -15,6 +15,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ruhvro_b200.h"
@@ -279,9 +280,8 @@ struct Arena {  // one decode call's output memory; shared by the result and eve
 
 struct rv_result {
     rv_schema* schema = nullptr;
-    std::shared_ptr<Arena> arena;
     std::vector<ChunkOut> chunks;
-    bool on_host = false;
+    std::vector<std::shared_ptr<Arena>> arenas;  // arenas[i] backs chunks[i] (one arena may back many chunks)
     int64_t arrow_bytes = 0;
     ~rv_result() { if (schema) rv_schema_release(schema); }
 };
@@ -303,7 +303,7 @@ const char* err_text(uint32_t code) {
 
 // ---- the decode call ------------------------------------------------------------------------
 rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d_offsets, int64_t n, int64_t num_chunks,
-                           int64_t total_bytes_hint, cudaStream_t stream, int device, rv_result** out) {
+                           int64_t total_bytes_hint, cudaStream_t stream, int device, rv_result** out, int64_t record_base = 0) {
     const Plan& plan = s->plan;
     const int S = int(plan.streams.size());
     const int n_slots = int(plan.slots.size());
@@ -316,10 +316,10 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
 
     auto res = std::make_unique<rv_result>();
     res->schema = rv_schema_retain(s);
-    res->arena = std::make_shared<Arena>();
-    res->arena->device = device;
+    auto arena_sp = std::make_shared<Arena>();
+    arena_sp->device = device;
 
-    for (int i = 0; i < 6; ++i) t_timings[i] = 0;
+    for (int i = 0; i < 4; ++i) t_timings[i] = 0;
     t_launches = 0;
 
     std::vector<unsigned long long> chunk_tot(size_t(k) * size_t(std::max(S, 1)), 0ull);
@@ -424,7 +424,7 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         RV_CUDA(cudaStreamSynchronize(stream));
         if (err_word != ~0ull) {
             const uint32_t code = uint32_t(err_word & 0xFF);
-            return fail(rv_status(code), std::string(err_text(code)) + " (record " + std::to_string(err_word >> 8) + ")");
+            return fail(rv_status(code), std::string(err_text(code)) + " (record " + std::to_string(int64_t(err_word >> 8) + record_base) + ")");
         }
     }
 
@@ -432,9 +432,10 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
     Layout L = compute_layout(plan, n, k, chunk_tot.data());
     res->chunks = std::move(L.chunks);
     const size_t zero_bytes = L.zero_bytes, total = L.total_bytes;
-    res->arena->bytes = total;
-    RV_CUDA(cudaMallocAsync(&res->arena->dev, std::max<size_t>(total, 64), stream));
-    uint8_t* arena = static_cast<uint8_t*>(res->arena->dev);
+    arena_sp->bytes = total;
+    RV_CUDA(cudaMallocAsync(&arena_sp->dev, std::max<size_t>(total, 64), stream));
+    uint8_t* arena = static_cast<uint8_t*>(arena_sp->dev);
+    res->arenas.assign(res->chunks.size(), arena_sp);
 
     if (n > 0) {
         if (zero_bytes) RV_CUDA(cudaMemsetAsync(arena, 0, zero_bytes, stream));
@@ -620,47 +621,47 @@ rv_status rv_decode_device(const rv_schema* s, const uint8_t* d_data, const int6
     }
 }
 
-rv_status rv_result_to_host(rv_result* r) {
-    if (!r) return fail(RV_ERR_INVALID, "null result");
-    if (r->on_host) return RV_OK;
-    Arena& a = *r->arena;
+}  // extern "C"
+
+namespace {
+
+// Copies one arena to a pinned host slab on `stream` (synchronises the stream).
+rv_status arena_to_host(Arena& a, cudaStream_t stream, float* ms) {
+    if (a.host) return RV_OK;
     size_t actual = 0;
     void* h = pinned().get(std::max<size_t>(a.bytes, 64), &actual);
     if (!h) return fail(RV_ERR_CUDA, "pinned host allocation failed");
-    a.host = h;
-    a.host_actual = actual;
     cudaEvent_t e0, e1;
     RV_CUDA(cudaEventCreate(&e0));
     RV_CUDA(cudaEventCreate(&e1));
-    cudaEventRecord(e0, nullptr);
-    cudaError_t e = cudaMemcpyAsync(h, a.dev, a.bytes, cudaMemcpyDeviceToHost, nullptr);
-    cudaEventRecord(e1, nullptr);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
-    cudaEventElapsedTime(&t_timings[5], e0, e1);
+    cudaEventRecord(e0, stream);
+    cudaError_t e = cudaMemcpyAsync(h, a.dev, a.bytes, cudaMemcpyDeviceToHost, stream);
+    cudaEventRecord(e1, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    float t = 0;
+    cudaEventElapsedTime(&t, e0, e1);
+    if (ms) *ms += t;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    if (e != cudaSuccess) return fail(RV_ERR_CUDA, std::string("device->host copy: ") + cudaGetErrorString(e));
-    r->on_host = true;
+    if (e != cudaSuccess) {
+        pinned().put(h, actual);
+        return fail(RV_ERR_CUDA, std::string("device->host copy: ") + cudaGetErrorString(e));
+    }
+    a.host = h;
+    a.host_actual = actual;
     return RV_OK;
 }
 
-rv_status rv_decode_host(const rv_schema* s, const uint8_t* data, const int64_t* offsets, int64_t n,
-                         int64_t num_chunks, rv_result** out) {
-    if (!out) return fail(RV_ERR_INVALID, "null argument");
-    *out = nullptr;
-    rv_status st = check_decodable(s);
-    if (st) return st;
-    if (n < 0 || (n > 0 && (!data || !offsets))) return fail(RV_ERR_INVALID, "bad input pointers");
-    int device = 0;
-    st = ensure_cuda(&device);
-    if (st) return st;
-    cudaStream_t stream = nullptr;
+// H2D of rows [r0, r1) of the caller's packed input, decode into `num_chunks` batches, D2H.
+rv_status decode_host_range(rv_schema* s, const uint8_t* data, const int64_t* offsets, int64_t r0, int64_t r1, int64_t num_chunks,
+                            cudaStream_t stream, int device, rv_result** out, float* h2d_ms, float* d2h_ms) {
+    const int64_t n = r1 - r0;
     DevBuf d_data, d_off;
     int64_t total = 0;
-    float h2d_ms = 0;
+    const uint8_t* base = nullptr;
     if (n > 0) {
-        const int64_t b0 = offsets[0];
-        total = offsets[n] - b0;
+        const int64_t b0 = offsets[r0];
+        total = offsets[r1] - b0;
         if (total < 0) return fail(RV_ERR_INVALID, "offsets are not monotonic");
         RV_CUDA(d_data.alloc(size_t(total) + 64, stream));
         RV_CUDA(d_off.alloc(size_t(n + 1) * 8, stream));
@@ -668,29 +669,129 @@ rv_status rv_decode_host(const rv_schema* s, const uint8_t* data, const int64_t*
         RV_CUDA(cudaEventCreate(&e0));
         RV_CUDA(cudaEventCreate(&e1));
         cudaEventRecord(e0, stream);
-        // The device copy keeps the caller's absolute offsets: d_data is biased so that
-        // d_data + offsets[i] addresses record i (offsets[0] need not be 0).
+        // The device copy keeps the caller's absolute offsets: the base pointer is biased so that
+        // base + offsets[i] addresses record i (kept 16-byte aligned by the b0 & 15 shift).
         cudaError_t e = cudaMemcpyAsync(static_cast<uint8_t*>(d_data.p) + (b0 & 15), data + b0, size_t(total), cudaMemcpyHostToDevice, stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_off.p, offsets, size_t(n + 1) * 8, cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_off.p, offsets + r0, size_t(n + 1) * 8, cudaMemcpyHostToDevice, stream);
         cudaEventRecord(e1, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        cudaEventElapsedTime(&h2d_ms, e0, e1);
+        float t = 0;
+        cudaEventElapsedTime(&t, e0, e1);
+        if (h2d_ms) *h2d_ms += t;
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
         if (e != cudaSuccess) return fail(RV_ERR_CUDA, std::string("host->device copy: ") + cudaGetErrorString(e));
+        base = static_cast<const uint8_t*>(d_data.p) + (b0 & 15) - b0;
     }
+    rv_status st;
     try {
-        // bias: kernel address of byte x is base + x, so base = copy_start - b0 (kept 16-byte aligned by the b0&15 shift)
-        const uint8_t* base = n > 0 ? static_cast<const uint8_t*>(d_data.p) + (offsets[0] & 15) - offsets[0] : nullptr;
-        st = decode_on_device(const_cast<rv_schema*>(s), base, static_cast<const int64_t*>(d_off.p), n, num_chunks, total, stream, device, out);
+        st = decode_on_device(s, base, static_cast<const int64_t*>(d_off.p), n, num_chunks, total, stream, device, out, r0);
     } catch (const std::exception& e) {
         return fail(RV_ERR_INVALID, e.what());
     }
     if (st) return st;
-    t_timings[4] = h2d_ms;
-    st = rv_result_to_host(*out);
+    st = arena_to_host(*(*out)->arenas[0], stream, d2h_ms);
     if (st) { rv_result_free(*out); *out = nullptr; }
     return st;
+}
+
+bool pipeline_enabled() {
+    const char* e = std::getenv("RV_PIPELINE");
+    return !(e && e[0] == '0');
+}
+
+}  // namespace
+
+extern "C" {
+
+rv_status rv_result_to_host(rv_result* r) {
+    if (!r) return fail(RV_ERR_INVALID, "null result");
+    float ms = 0;
+    for (auto& a : r->arenas) {
+        rv_status st = arena_to_host(*a, nullptr, &ms);
+        if (st) return st;
+    }
+    t_timings[5] = ms;
+    return RV_OK;
+}
+
+rv_status rv_decode_host(const rv_schema* s_, const uint8_t* data, const int64_t* offsets, int64_t n,
+                         int64_t num_chunks, rv_result** out) {
+    if (!out) return fail(RV_ERR_INVALID, "null argument");
+    *out = nullptr;
+    rv_schema* s = const_cast<rv_schema*>(s_);
+    rv_status st = check_decodable(s);
+    if (st) return st;
+    if (n < 0 || (n > 0 && (!data || !offsets))) return fail(RV_ERR_INVALID, "bad input pointers");
+    int device = 0;
+    st = ensure_cuda(&device);
+    if (st) return st;
+    const int64_t k = clamp_chunks(num_chunks, n);
+    float h2d = 0, d2h = 0;
+    if (k < 2 || n < 65536 || !pipeline_enabled()) {
+        st = decode_host_range(s, data, offsets, 0, n, num_chunks, nullptr, device, out, &h2d, &d2h);
+        t_timings[4] = h2d;
+        t_timings[5] = d2h;
+        return st;
+    }
+    // Chunks are independent batches (deserialize.rs:57-68,92-119): decode them on a few worker streams so
+    // the H2D copy of chunk i+1 overlaps the kernels and the D2H copy of chunk i (full-duplex PCIe).  This
+    // is the GPU-side analogue of the reference fanning chunks out to its thread pool.
+    const int64_t chunk_rows = n / k;
+    std::vector<rv_result*> parts(size_t(k), nullptr);
+    std::vector<rv_status> status(size_t(k), RV_OK);
+    std::vector<std::string> message{size_t(k), std::string()};
+    std::atomic<int64_t> next{0};
+    std::mutex acc_mu;
+    float acc[6] = {0, 0, 0, 0, 0, 0};
+    int acc_launches = 0;
+    const char* walker = "none";
+    auto worker = [&]() {
+        cudaSetDevice(device);
+        cudaStream_t stream = nullptr;
+        if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) stream = nullptr;
+        for (;;) {
+            const int64_t i = next.fetch_add(1);
+            if (i >= k) break;
+            const int64_t r0 = i * chunk_rows, r1 = (i == k - 1) ? n : r0 + chunk_rows;
+            float hm = 0, dm = 0;
+            status[size_t(i)] = decode_host_range(s, data, offsets, r0, r1, 1, stream, device, &parts[size_t(i)], &hm, &dm);
+            if (status[size_t(i)]) message[size_t(i)] = t_error;
+            std::lock_guard<std::mutex> g(acc_mu);
+            for (int q = 0; q < 4; ++q) acc[q] += t_timings[q];
+            acc[4] += hm;
+            acc[5] += dm;
+            acc_launches += t_launches;
+            walker = t_walker;
+        }
+        if (stream) cudaStreamDestroy(stream);
+    };
+    const int n_workers = int(std::min<int64_t>(k, 3));
+    std::vector<std::thread> threads;
+    for (int w = 0; w < n_workers; ++w) threads.emplace_back(worker);
+    for (auto& t : threads) t.join();
+    for (int q = 0; q < 6; ++q) t_timings[q] = acc[q];
+    t_launches = acc_launches;
+    t_walker = walker;
+    auto res = std::make_unique<rv_result>();
+    res->schema = rv_schema_retain(s);
+    rv_status first = RV_OK;
+    for (int64_t i = 0; i < k; ++i) {
+        if (status[size_t(i)] && !first) { first = status[size_t(i)]; t_error = message[size_t(i)]; }  // first failing chunk wins (:115-119)
+    }
+    for (int64_t i = 0; i < k; ++i) {
+        rv_result* part = parts[size_t(i)];
+        if (!part) continue;
+        if (!first) {
+            res->chunks.push_back(std::move(part->chunks[0]));
+            res->arenas.push_back(part->arenas[0]);
+            res->arrow_bytes += part->arrow_bytes;
+        }
+        rv_result_free(part);
+    }
+    if (first) return first;
+    *out = res.release();
+    return RV_OK;
 }
 
 int64_t rv_result_num_batches(const rv_result* r) { return r ? int64_t(r->chunks.size()) : 0; }
@@ -699,17 +800,26 @@ int64_t rv_result_num_rows(const rv_result* r, int64_t batch) {
     return r->chunks[size_t(batch)].rows;
 }
 int64_t rv_result_arrow_bytes(const rv_result* r) { return r ? r->arrow_bytes : 0; }
-int64_t rv_result_buffer_bytes(const rv_result* r) { return r ? int64_t(r->arena->bytes) : 0; }
+int64_t rv_result_buffer_bytes(const rv_result* r) {
+    if (!r) return 0;
+    int64_t total = 0;
+    const Arena* last = nullptr;
+    for (auto& a : r->arenas) {
+        if (a.get() != last) total += int64_t(a->bytes);
+        last = a.get();
+    }
+    return total;
+}
 
 rv_status rv_result_export(rv_result* r, int64_t batch, struct ArrowArray* out_array, struct ArrowSchema* out_schema) {
     if (!r || !out_array) return fail(RV_ERR_INVALID, "null argument");
     if (batch < 0 || batch >= int64_t(r->chunks.size())) return fail(RV_ERR_INVALID, "batch index out of range");
-    if (!r->on_host) return fail(RV_ERR_INVALID, "result is device-resident: call rv_result_to_host() or rv_result_export_device()");
+    if (!r->arenas[size_t(batch)]->host) return fail(RV_ERR_INVALID, "result is device-resident: call rv_result_to_host() or rv_result_export_device()");
     if (out_schema) {
         rv_status st = rv_schema_export_arrow(r->schema, out_schema);
         if (st) return st;
     }
-    export_batch(r->schema->plan, r->chunks[size_t(batch)], static_cast<const uint8_t*>(r->arena->host), r->arena, out_array);
+    export_batch(r->schema->plan, r->chunks[size_t(batch)], static_cast<const uint8_t*>(r->arenas[size_t(batch)]->host), r->arenas[size_t(batch)], out_array);
     return RV_OK;
 }
 
@@ -720,8 +830,8 @@ rv_status rv_result_export_device(rv_result* r, int64_t batch, struct ArrowDevic
         rv_status st = rv_schema_export_arrow(r->schema, out_schema);
         if (st) return st;
     }
-    export_batch(r->schema->plan, r->chunks[size_t(batch)], static_cast<const uint8_t*>(r->arena->dev), r->arena, &out_array->array);
-    out_array->device_id = r->arena->device;
+    export_batch(r->schema->plan, r->chunks[size_t(batch)], static_cast<const uint8_t*>(r->arenas[size_t(batch)]->dev), r->arenas[size_t(batch)], &out_array->array);
+    out_array->device_id = r->arenas[size_t(batch)]->device;
     out_array->device_type = ARROW_DEVICE_CUDA;
     out_array->sync_event = nullptr;  // the decode call synchronised its stream before returning
     out_array->reserved[0] = out_array->reserved[1] = out_array->reserved[2] = 0;

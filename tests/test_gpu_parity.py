@@ -115,6 +115,29 @@ def test_benchmark_workloads_small(coracle, walker):
         assert pr.last_walker() == walker
 
 
+def test_pipelined_chunks_large_batch(coracle, walker):
+    """n >= 65536 with num_chunks > 1 takes the pipelined rv_decode_host path (H2D / decode / D2H of
+    different chunks overlapped on worker streams); results and error reporting must not change."""
+    import workloads
+    sj, data, off = workloads.generate("kafka", 300_000, seed=11)
+    for k in (2, 8, 13):
+        assert_matches_oracle(coracle, pr.decode_packed(data, off, 300_000, sj, k), sj, data, off, 300_000, k, full_validate=False)
+    from tests import malformed as M
+    good = [M.good_record(i) for i in range(200_000)]
+    for pos in (5, 70_123, 199_999):
+        recs = list(good)
+        recs[pos] = b"\x80"
+        with pytest.raises(ValueError) as e:
+            pr.deserialize_array_threaded(recs, M.FLAT, 8)
+        assert f"(record {pos})" in str(e.value), str(e.value)
+    recs = list(good)
+    recs[150_000] = b"\x80"
+    recs[20_000] = b"\xff" * 11
+    with pytest.raises(ValueError) as e:
+        pr.deserialize_array_threaded(recs, M.FLAT, 8)
+    assert "(record 20000)" in str(e.value) and "varint" in str(e.value)   # first failing chunk wins
+
+
 def test_error_surface():
     with pytest.raises(TypeError):
         pr.deserialize_array([b"ok", "not-bytes"], G.G1_SCHEMA)
