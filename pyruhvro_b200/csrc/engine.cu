@@ -109,6 +109,78 @@ class PinnedCache {
     size_t cached_ = 0;
 };
 
+// ------------------------------------------------------------------------------------------
+// device memory: size-bucketed cache over cudaMalloc.  Blocks are only returned once the work that
+// used them has been synchronised (every decode path syncs its stream before its buffers die; arenas
+// die after their batches are released), so reuse across streams and threads needs no stream ordering.
+// ------------------------------------------------------------------------------------------
+class DeviceCache {
+  public:
+    void* get(size_t bytes, int device, size_t* actual) {
+        const size_t want = round(bytes);
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            auto& fl = free_[device];
+            auto it = fl.lower_bound(want);
+            if (it != fl.end() && it->first <= want + want / 4 + (size_t(1) << 20)) {
+                void* p = it->second;
+                *actual = it->first;
+                cached_ -= it->first;
+                fl.erase(it);
+                return p;
+            }
+        }
+        void* p = nullptr;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            (void)cudaGetLastError();
+            trim(device);
+            if (cudaMalloc(&p, want) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+        }
+        *actual = want;
+        return p;
+    }
+    void put(void* p, size_t actual, int device) {
+        if (!p) return;
+        std::lock_guard<std::mutex> g(mu_);
+        free_[device].emplace(actual, p);
+        cached_ += actual;
+    }
+    void trim(int device) {
+        std::lock_guard<std::mutex> g(mu_);
+        auto& fl = free_[device];
+        for (auto& kv : fl) { cudaFree(kv.second); cached_ -= kv.first; }
+        fl.clear();
+    }
+
+  private:
+    static size_t round(size_t b) {
+        const size_t g = b >= (size_t(32) << 20) ? (size_t(4) << 20) : (b >= (size_t(1) << 20) ? (size_t(256) << 10) : 4096);
+        return ((b ? b : 1) + g - 1) / g * g;
+    }
+    std::mutex mu_;
+    std::map<int, std::multimap<size_t, void*>> free_;
+    size_t cached_ = 0;
+};
+
+DeviceCache& devmem() {
+    static DeviceCache* c = new DeviceCache();  // intentionally leaked
+    return *c;
+}
+
+// Worker streams of the chunk pipeline (created once per device).
+cudaStream_t worker_stream(int device, int w) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, cudaStream_t> streams;
+    std::lock_guard<std::mutex> g(mu);
+    auto key = std::make_pair(device, w);
+    auto it = streams.find(key);
+    if (it != streams.end()) return it->second;
+    cudaStream_t s = nullptr;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) s = nullptr;
+    streams[key] = s;
+    return s;
+}
+
 std::mutex g_host_mu;
 std::map<void*, size_t> g_host_sizes;  // rv_host_alloc blocks -> slab size
 
@@ -141,14 +213,16 @@ rv_status ensure_cuda(int* device) {
     return RV_OK;
 }
 
-struct DevBuf {  // stream-ordered device allocation, freed on scope exit unless released
+struct DevBuf {  // cached device allocation, returned on scope exit (after the owning stream was synchronised)
     void* p = nullptr;
-    cudaStream_t s = nullptr;
-    cudaError_t alloc(size_t bytes, cudaStream_t st) {
-        s = st;
-        return cudaMallocAsync(&p, bytes ? bytes : 1, st);
+    size_t actual = 0;
+    int device = 0;
+    cudaError_t alloc(size_t bytes, cudaStream_t) {
+        if (cudaGetDevice(&device) != cudaSuccess) return cudaErrorInvalidDevice;
+        p = devmem().get(bytes, device, &actual);
+        return p ? cudaSuccess : cudaErrorMemoryAllocation;
     }
-    ~DevBuf() { if (p) cudaFreeAsync(p, s); }
+    ~DevBuf() { if (p) devmem().put(p, actual, device); }
 };
 
 }  // namespace
@@ -260,18 +334,13 @@ namespace {
 
 struct Arena {  // one decode call's output memory; shared by the result and every exported batch
     void* dev = nullptr;
+    size_t dev_actual = 0;
     size_t bytes = 0;
     void* host = nullptr;
     size_t host_actual = 0;
     int device = 0;
     ~Arena() {
-        if (dev) {
-            int cur = 0;
-            cudaGetDevice(&cur);
-            if (cur != device) cudaSetDevice(device);
-            cudaFreeAsync(dev, nullptr);
-            if (cur != device) cudaSetDevice(cur);
-        }
+        if (dev) devmem().put(dev, dev_actual, device);
         if (host) pinned().put(host, host_actual);
     }
 };
@@ -433,7 +502,8 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
     res->chunks = std::move(L.chunks);
     const size_t zero_bytes = L.zero_bytes, total = L.total_bytes;
     arena_sp->bytes = total;
-    RV_CUDA(cudaMallocAsync(&arena_sp->dev, std::max<size_t>(total, 64), stream));
+    arena_sp->dev = devmem().get(std::max<size_t>(total, 64), device, &arena_sp->dev_actual);
+    if (!arena_sp->dev) return fail(RV_ERR_CUDA, "device allocation of the Arrow buffer arena failed (" + std::to_string(total) + " bytes)");
     uint8_t* arena = static_cast<uint8_t*>(arena_sp->dev);
     res->arenas.assign(res->chunks.size(), arena_sp);
 
@@ -746,10 +816,9 @@ rv_status rv_decode_host(const rv_schema* s_, const uint8_t* data, const int64_t
     float acc[6] = {0, 0, 0, 0, 0, 0};
     int acc_launches = 0;
     const char* walker = "none";
-    auto worker = [&]() {
+    auto worker = [&](int wid) {
         cudaSetDevice(device);
-        cudaStream_t stream = nullptr;
-        if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) stream = nullptr;
+        cudaStream_t stream = worker_stream(device, wid);
         for (;;) {
             const int64_t i = next.fetch_add(1);
             if (i >= k) break;
@@ -764,11 +833,10 @@ rv_status rv_decode_host(const rv_schema* s_, const uint8_t* data, const int64_t
             acc_launches += t_launches;
             walker = t_walker;
         }
-        if (stream) cudaStreamDestroy(stream);
     };
     const int n_workers = int(std::min<int64_t>(k, 3));
     std::vector<std::thread> threads;
-    for (int w = 0; w < n_workers; ++w) threads.emplace_back(worker);
+    for (int w = 0; w < n_workers; ++w) threads.emplace_back(worker, w);
     for (auto& t : threads) t.join();
     for (int q = 0; q < 6; ++q) t_timings[q] = acc[q];
     t_launches = acc_launches;
