@@ -834,7 +834,9 @@ rv_status rv_decode_host(const rv_schema* s_, const uint8_t* data, const int64_t
             walker = t_walker;
         }
     };
-    const int n_workers = int(std::min<int64_t>(k, 3));
+    int want_workers = 4;
+    if (const char* ev = std::getenv("RV_WORKERS")) want_workers = std::max(1, std::atoi(ev));
+    const int n_workers = int(std::min<int64_t>(k, want_workers));
     std::vector<std::thread> threads;
     for (int w = 0; w < n_workers; ++w) threads.emplace_back(worker, w);
     for (auto& t : threads) t.join();
