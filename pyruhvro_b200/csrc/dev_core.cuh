@@ -39,7 +39,8 @@ struct WalkCtx {
     uint64_t usel;         // interpreter: selected variant per union nesting level (8 bits each)
     const DNode* nodes;    // interpreter: the plan
     uint32_t* cur;         // per-lane cursors: cur[stream * kBlock]
-    void* const* bufs;     // slot -> buffer of this chunk
+    void* const* bufs;     // slot -> buffer of this chunk (global memory table)
+    uint32_t ptrs_soff;    // device emit: offset inside rv_smem of the CTA's copy of that table (0: none)
     const int32_t* sym_off;
     const uint8_t* sym_bytes;
     bool stage_on;         // emit: Utf8 bytes go to the shared-memory staging area
@@ -66,68 +67,86 @@ RV_HD uint32_t ld_u8(const C& c, uint32_t pos) {
     return c.base[pos];
 }
 
+// Arrow buffer of `slot`.  The emit CTAs keep this chunk's pointer table in shared memory: a record walk
+// dereferences ~30 of them and a global (L1) load each time is a long-scoreboard stall on the lane's
+// critical path.
+template <class C>
+RV_HD void* buf_ptr(const C& c, int slot) {
+#if defined(__CUDA_ARCH__)
+    if (c.ptrs_soff) return *reinterpret_cast<void* const*>(rv_smem + c.ptrs_soff + uint32_t(slot) * 8u);
+#endif
+    return c.bufs[slot];
+}
+
 RV_HD int64_t zz32(uint32_t r) { return int64_t(int32_t((r >> 1) ^ (0u - (r & 1u)))); }
 RV_HD int64_t zz64(uint64_t r) { return int64_t(r >> 1) ^ -int64_t(r & 1); }
 
 // read_zigzag_long (fast_decode.rs:854-869).  One-byte varints (branch indices, short lengths, small
 // ints: the bulk of real records) take a branch-light fast path; everything else goes through the
 // reference's byte loop.
-template <class C>
+//
+// CHECK = false is used by the EMIT walk only: it runs after the count kernel walked the very same bytes
+// with CHECK = true (and the call was aborted on any error), so bounds / range checks would only re-prove
+// what is known.  (Inputs are borrowed for the duration of the call and must not be mutated meanwhile.)
+template <bool CHECK = true, class C>
 RV_HD int64_t rd_varint(C& c) {
-    if (c.pos < c.end) {
+    if (!CHECK || c.pos < c.end) {
         const uint32_t b = ld_u8(c, c.pos);
         if (b < 0x80u) { c.pos += 1; return zz32(b); }
     }
     uint64_t r = 0;
     uint32_t shift = 0;
     for (;;) {
-        if (c.pos >= c.end) { fail(c, E_EOF); return 0; }
+        if (CHECK && c.pos >= c.end) { fail(c, E_EOF); return 0; }
         const uint32_t b = ld_u8(c, c.pos++);
         r |= uint64_t(b & 0x7Fu) << shift;
         if (!(b & 0x80u)) break;
         shift += 7;
-        if (shift >= 64) { fail(c, E_VARINT); return 0; }
+        if (CHECK && shift >= 64) { fail(c, E_VARINT); return 0; }
+        if (!CHECK && shift >= 70) break;  // unreachable on validated input; bounds the loop regardless
     }
     return zz64(r);
 }
 
 // Length prefix of a string (read_string, fast_decode.rs:902-911): false on error.
-template <class C>
+template <bool CHECK = true, class C>
 RV_HD bool rd_len(C& c, uint32_t& len) {
     bool have = false;
-    if (c.pos < c.end) {
+    if (!CHECK || c.pos < c.end) {
         const uint32_t b = ld_u8(c, c.pos);
         if (b < 0x80u) {  // one byte: zigzag(len) < 128, odd = negative
             c.pos += 1;
-            if (b & 1u) { fail(c, E_NEG_LEN); return false; }
+            if (CHECK && (b & 1u)) { fail(c, E_NEG_LEN); return false; }
             len = b >> 1;
             have = true;
         }
     }
     if (!have) {
-        const int64_t l = rd_varint(c);
-        if (c.err) return false;
-        if (l < 0) { fail(c, E_NEG_LEN); return false; }
-        if (l > int64_t(0xFFFFFFFFu)) { fail(c, E_EOF); return false; }
+        const int64_t l = rd_varint<CHECK>(c);
+        if (CHECK) {
+            if (c.err) return false;
+            if (l < 0) { fail(c, E_NEG_LEN); return false; }
+            if (l > int64_t(0xFFFFFFFFu)) { fail(c, E_EOF); return false; }
+        }
         len = uint32_t(l);
     }
-    if (len > c.end - c.pos) { fail(c, E_EOF); return false; }
+    if (CHECK && len > c.end - c.pos) { fail(c, E_EOF); return false; }
     return true;
 }
 
 // union_branch (fast_decode.rs:585-593): true = Value, false = Null (or error).
-template <class C>
+template <bool CHECK = true, class C>
 RV_HD bool rd_branch(C& c, bool null_first) {
-    if (c.pos < c.end) {
+    if (!CHECK || c.pos < c.end) {
         const uint32_t b = ld_u8(c, c.pos);
         if (b == 0u || b == 2u) {  // canonical one-byte encodings of branch 0 / 1
             c.pos += 1;
             return (b == 2u) == null_first;
         }
     }
-    const int64_t idx = rd_varint(c);
-    if (c.err) return false;
-    if (idx == 0 || idx == 1) return (idx == 1) == null_first;
+    const int64_t idx = rd_varint<CHECK>(c);
+    if (CHECK && c.err) return false;
+    if (!CHECK || idx == 0 || idx == 1) return (idx == 1) == null_first;
     fail(c, E_BRANCH);
     return false;
 }
@@ -140,12 +159,12 @@ RV_HD void put_bit(C& c, int slot, uint32_t row, bool bit) {
 #if defined(__CUDA_ARCH__)
     if (D == 0) {
         const unsigned w = __ballot_sync(0xFFFFFFFFu, bit);
-        if (c.store_word) static_cast<uint32_t*>(c.bufs[slot])[row >> 5] = w;
+        if (c.store_word) static_cast<uint32_t*>(buf_ptr(c, slot))[row >> 5] = w;
     } else {
-        if (bit) atomicOr(static_cast<unsigned int*>(c.bufs[slot]) + (row >> 5), 1u << (row & 31));
+        if (bit) atomicOr(static_cast<unsigned int*>(buf_ptr(c, slot)) + (row >> 5), 1u << (row & 31));
     }
 #else
-    if (bit && (D > 0 || c.in_range)) static_cast<uint8_t*>(c.bufs[slot])[row >> 3] |= uint8_t(1u << (row & 7));
+    if (bit && (D > 0 || c.in_range)) static_cast<uint8_t*>(buf_ptr(c, slot))[row >> 3] |= uint8_t(1u << (row & 7));
 #endif
 }
 
@@ -156,9 +175,9 @@ RV_HD bool may_store(const C& c) { return (D > 0) || c.in_range; }
 template <int MODE, int D, class C>
 RV_HD void op_i32(C& c, bool valid, int slot_a, int slot_v, uint32_t row) {
     int32_t v = 0;
-    if (valid) { const int64_t x = rd_varint(c); if (!c.err) v = int32_t(x); else valid = false; }
+    if (valid) { const int64_t x = rd_varint<MODE == WM_COUNT>(c); if (MODE == WM_EMIT || !c.err) v = int32_t(x); else valid = false; }
     if (MODE == WM_EMIT) {
-        if (may_store<D>(c)) static_cast<int32_t*>(c.bufs[slot_a])[row] = v;
+        if (may_store<D>(c)) static_cast<int32_t*>(buf_ptr(c, slot_a))[row] = v;
         if (slot_v >= 0) put_bit<D>(c, slot_v, row, valid);
     }
 }
@@ -166,9 +185,9 @@ RV_HD void op_i32(C& c, bool valid, int slot_a, int slot_v, uint32_t row) {
 template <int MODE, int D, class C>
 RV_HD void op_i64(C& c, bool valid, int slot_a, int slot_v, uint32_t row) {
     int64_t v = 0;
-    if (valid) { const int64_t x = rd_varint(c); if (!c.err) v = x; else valid = false; }
+    if (valid) { const int64_t x = rd_varint<MODE == WM_COUNT>(c); if (MODE == WM_EMIT || !c.err) v = x; else valid = false; }
     if (MODE == WM_EMIT) {
-        if (may_store<D>(c)) static_cast<int64_t*>(c.bufs[slot_a])[row] = v;
+        if (may_store<D>(c)) static_cast<int64_t*>(buf_ptr(c, slot_a))[row] = v;
         if (slot_v >= 0) put_bit<D>(c, slot_v, row, valid);
     }
 }
@@ -177,7 +196,7 @@ template <int MODE, int D, class C>
 RV_HD void op_f32(C& c, bool valid, int slot_a, int slot_v, uint32_t row) {  // read_f32 :871-879
     uint32_t v = 0;
     if (valid) {
-        if (c.end - c.pos < 4u) { fail(c, E_EOF); valid = false; }
+        if (MODE == WM_COUNT && c.end - c.pos < 4u) { fail(c, E_EOF); valid = false; }
         else {
             if (MODE == WM_EMIT) {
                 const uint32_t p = c.pos;
@@ -187,7 +206,7 @@ RV_HD void op_f32(C& c, bool valid, int slot_a, int slot_v, uint32_t row) {  // 
         }
     }
     if (MODE == WM_EMIT) {
-        if (may_store<D>(c)) static_cast<uint32_t*>(c.bufs[slot_a])[row] = v;
+        if (may_store<D>(c)) static_cast<uint32_t*>(buf_ptr(c, slot_a))[row] = v;
         if (slot_v >= 0) put_bit<D>(c, slot_v, row, valid);
     }
 }
@@ -196,7 +215,7 @@ template <int MODE, int D, class C>
 RV_HD void op_f64(C& c, bool valid, int slot_a, int slot_v, uint32_t row) {  // read_f64 :881-891
     uint64_t v = 0;
     if (valid) {
-        if (c.end - c.pos < 8u) { fail(c, E_EOF); valid = false; }
+        if (MODE == WM_COUNT && c.end - c.pos < 8u) { fail(c, E_EOF); valid = false; }
         else {
             if (MODE == WM_EMIT) {
                 const uint32_t p = c.pos;
@@ -208,7 +227,7 @@ RV_HD void op_f64(C& c, bool valid, int slot_a, int slot_v, uint32_t row) {  // 
         }
     }
     if (MODE == WM_EMIT) {
-        if (may_store<D>(c)) static_cast<uint64_t*>(c.bufs[slot_a])[row] = v;
+        if (may_store<D>(c)) static_cast<uint64_t*>(buf_ptr(c, slot_a))[row] = v;
         if (slot_v >= 0) put_bit<D>(c, slot_v, row, valid);
     }
 }
@@ -217,10 +236,10 @@ template <int MODE, int D, class C>
 RV_HD void op_bool(C& c, bool valid, int slot_a, int slot_v, uint32_t row) {  // read_bool :893-900
     bool v = false;
     if (valid) {
-        if (c.pos >= c.end) { fail(c, E_EOF); valid = false; }
+        if (MODE == WM_COUNT && c.pos >= c.end) { fail(c, E_EOF); valid = false; }
         else {
             const uint32_t b = ld_u8(c, c.pos++);
-            if (b > 1u) { fail(c, E_BOOL); valid = false; } else v = b != 0u;
+            if (MODE == WM_COUNT && b > 1u) { fail(c, E_BOOL); valid = false; } else v = b != 0u;
         }
     }
     if (MODE == WM_EMIT) {
@@ -275,7 +294,7 @@ RV_HD void copy_from_record(C& c, int slot_b, int stream, uint32_t o, uint32_t s
     }
 #endif
     (void)stream;
-    uint8_t* dst = static_cast<uint8_t*>(c.bufs[slot_b]) + o;
+    uint8_t* dst = static_cast<uint8_t*>(buf_ptr(c, slot_b)) + o;
     for (uint32_t i = 0; i < len; ++i) dst[i] = uint8_t(ld_u8(c, s + i));
 }
 
@@ -289,7 +308,7 @@ RV_HD void copy_from_symbols(C& c, int slot_b, int stream, uint32_t o, const uin
     }
 #endif
     (void)stream;
-    uint8_t* dst = static_cast<uint8_t*>(c.bufs[slot_b]) + o;
+    uint8_t* dst = static_cast<uint8_t*>(buf_ptr(c, slot_b)) + o;
     for (uint32_t i = 0; i < len; ++i) dst[i] = src[i];
 }
 
@@ -302,7 +321,7 @@ RV_HD void utf8_finish(C& c, bool valid, uint32_t len, int slot_a, int slot_v, i
         cur = nxt;
     } else {
         const uint32_t o = cur + len;
-        if (may_store<D>(c)) static_cast<int32_t*>(c.bufs[slot_a])[row + 1] = int32_t(o);
+        if (may_store<D>(c)) static_cast<int32_t*>(buf_ptr(c, slot_a))[row + 1] = int32_t(o);
         cur = o;
         if (slot_v >= 0) put_bit<D>(c, slot_v, row, valid);
     }
@@ -312,7 +331,7 @@ template <int MODE, int D, class C>
 RV_HD void op_str(C& c, bool valid, int slot_a, int slot_b, int slot_v, int stream, uint32_t row) {  // read_string :902-922
     uint32_t len = 0;
     if (valid) {
-        if (!rd_len(c, len)) { valid = false; len = 0; }
+        if (!rd_len<MODE == WM_COUNT>(c, len)) { valid = false; len = 0; }
         else {
             if (MODE == WM_EMIT && len) copy_from_record(c, slot_b, stream, c.cur[uint32_t(stream) * kBlock], c.pos, len);
             c.pos += len;
@@ -325,9 +344,9 @@ template <int MODE, int D, class C>
 RV_HD void op_enum(C& c, bool valid, int slot_a, int slot_b, int slot_v, int stream, uint32_t row, int sym_base, int n_sym) {  // append_enum :570-578
     uint32_t len = 0;
     if (valid) {
-        const int64_t l = rd_varint(c);
-        if (c.err) valid = false;
-        else if (uint64_t(l) >= uint64_t(uint32_t(n_sym))) { fail(c, E_ENUM); valid = false; }
+        const int64_t l = rd_varint<MODE == WM_COUNT>(c);
+        if (MODE == WM_COUNT && c.err) valid = false;
+        else if (MODE == WM_COUNT && uint64_t(l) >= uint64_t(uint32_t(n_sym))) { fail(c, E_ENUM); valid = false; }
         else {
             const int32_t b0 = c.sym_off[sym_base + int32_t(l)];
             len = uint32_t(c.sym_off[sym_base + int32_t(l) + 1] - b0);
@@ -344,32 +363,33 @@ template <int MODE, int D, class C>
 RV_HD int op_union(C& c, bool valid, int n_variants, int slot_a, uint32_t row) {
     int sel = -1;
     if (valid) {
-        const int64_t idx = rd_varint(c);
-        if (!c.err) {
+        const int64_t idx = rd_varint<MODE == WM_COUNT>(c);
+        if (MODE == WM_EMIT) sel = int(idx);
+        else if (!c.err) {
             if (idx < 0 || idx >= int64_t(n_variants)) fail(c, E_BRANCH);
             else sel = int(idx);
         }
     }
-    if (MODE == WM_EMIT && may_store<D>(c)) static_cast<int8_t*>(c.bufs[slot_a])[row] = int8_t(sel < 0 ? 0 : sel);
+    if (MODE == WM_EMIT && may_store<D>(c)) static_cast<int8_t*>(buf_ptr(c, slot_a))[row] = int8_t(sel < 0 ? 0 : sel);
     return sel;
 }
 
 // read_block_count (:689-700) inside the item loop of ListDecoder / MapDecoder (:703-719,745-762).
 // Returns 0: list ended or error (leave the loop); 1: `rem` items follow; 2: a zero-width block was
 // folded into `total` (read the next block header).
-template <class C>
+template <bool CHECK = true, class C>
 RV_HD int rd_block(C& c, int64_t& rem, uint32_t& total, bool zero_items) {
-    int64_t n = rd_varint(c);
-    if (c.err) return 0;
+    int64_t n = rd_varint<CHECK>(c);
+    if (CHECK && c.err) return 0;
     if (n < 0) {
-        (void)rd_varint(c);  // block byte size: ignored, the items are always walked
-        if (c.err) return 0;
+        (void)rd_varint<CHECK>(c);  // block byte size: ignored, the items are always walked
+        if (CHECK && c.err) return 0;
         n = int64_t(0 - uint64_t(n));
         if (n < 0) return 2;  // i64::MIN: `0..n` is an empty range in the reference
     }
     if (n == 0) return 0;
     if (zero_items) {  // items are zero bytes wide and own no buffers: no need to iterate
-        if (n > int64_t(0x7FFFFFFF) - int64_t(total)) { fail(c, E_OVERFLOW); return 0; }
+        if (CHECK && n > int64_t(0x7FFFFFFF) - int64_t(total)) { fail(c, E_OVERFLOW); return 0; }
         total += uint32_t(n);
         return 2;
     }
@@ -386,7 +406,7 @@ RV_HD void list_finish(C& c, bool valid, uint32_t first_row, uint32_t total, int
         cur = nxt;
     } else {
         cur = first_row + total;
-        if (may_store<D>(c)) static_cast<int32_t*>(c.bufs[slot_a])[row + 1] = int32_t(first_row + total);
+        if (may_store<D>(c)) static_cast<int32_t*>(buf_ptr(c, slot_a))[row + 1] = int32_t(first_row + total);
         if (slot_v >= 0) put_bit<D>(c, slot_v, row, valid);
     }
 }

@@ -10,7 +10,7 @@
 //               values / offsets are stored row-aligned; space-0 validity is one ballot word per warp.
 //
 // Shared-memory map (dynamic, rv_smem):
-//   [nodes n_nodes*32][cur S*256*4][wtot S*8*4 (emit: tile bases)][tot (S+1)*4][adj S*4][in: smem_data_cap][out: smem_stage_cap]
+//   [nodes n_nodes*32][cur S*256*4][wtot S*8*4 (emit: tile bases)][tot (S+1)*4][adj S*4][ptrs n_slots*8][in: smem_data_cap][out: smem_stage_cap]
 #pragma once
 #include "dev_core.cuh"
 
@@ -60,6 +60,10 @@ __device__ __forceinline__ TileWindow stage_in(const DecodeParams& p, const Tile
     }
     uint32_t* cur = reinterpret_cast<uint32_t*>(rv_smem + m.cur);
     if (EMIT) {
+        // this chunk's Arrow buffer pointers (see buf_ptr)
+        void** sp = reinterpret_cast<void**>(rv_smem + m.ptrs);
+        void* const* gp = p.bufs + size_t(t.chunk) * p.n_slots;
+        for (int i = tid; i < p.n_slots; i += kBlock) sp[i] = gp[i];
         const uint32_t* lo = p.lane_off + size_t(tile_id) * p.n_streams * kBlock;
         for (int s = 0; s < p.n_streams; ++s)
             cur[s * kBlock + tid] = __ldg(lo + s * kBlock + tid) + __ldg(p.tile_base + size_t(s) * p.n_tiles + tile_id);
@@ -91,6 +95,7 @@ __device__ __forceinline__ int64_t init_ctx(C& c, const DecodeParams& p, const T
     c.sym_off = p.sym_off;
     c.sym_bytes = p.sym_bytes;
     c.bufs = p.bufs ? p.bufs + size_t(t.chunk) * p.n_slots : nullptr;
+    c.ptrs_soff = p.bufs ? m.ptrs : 0u;
     c.err = 0;
     c.pm = 0;
     c.usel = 0;
@@ -137,7 +142,7 @@ __device__ __forceinline__ void count_walk(const DecodeParams& p, const Tile& t,
 template <class W, bool GENERIC>
 __device__ __forceinline__ void count_body(const DecodeParams& p, const int tile_id) {
     const Tile t = tile_of(p, tile_id);
-    const SmemMap m = smem_map(p.n_nodes, p.n_streams, p.smem_data_cap);
+    const SmemMap m = smem_map(p.n_nodes, p.n_streams, p.n_slots, p.smem_data_cap);
     const TileWindow w = stage_in<false>(p, t, tile_id, m);
     __syncthreads();
     if (w.staged) count_walk<W, true>(p, t, m, w);
@@ -195,7 +200,7 @@ __device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t,
         tbase[tid] = tb;
         tot[tid] = __ldg(p.tile_agg + size_t(tid) * p.n_tiles + tile_id);
         const int slot = p.stream_slot[tid];
-        tbase[p.n_streams + tid] = slot >= 0 ? uint32_t(reinterpret_cast<uintptr_t>(static_cast<uint8_t*>(c.bufs[slot]) + tb) & 15u) : 0u;
+        tbase[p.n_streams + tid] = slot >= 0 ? uint32_t(reinterpret_cast<uintptr_t>(static_cast<uint8_t*>(buf_ptr(c, slot)) + tb) & 15u) : 0u;
     }
     __syncthreads();
     // Staging map of the Utf8 streams.  Stream s's bytes of this tile occupy [tile_base, tile_base + tot)
@@ -224,7 +229,7 @@ __device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t,
             for (int i = tid; i < p.n_nodes; i += kBlock) {
                 const DNode nd = c.nodes[i];
                 if (nd.kind == NK_STR || nd.kind == NK_ENUM || nd.kind == NK_LIST || nd.kind == NK_MAP)
-                    static_cast<int32_t*>(c.bufs[nd.slot_a])[0] = 0;
+                    static_cast<int32_t*>(buf_ptr(c, nd.slot_a))[0] = 0;
             }
         } else {
             W::zero_offsets(c, tid);
@@ -240,7 +245,7 @@ __device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t,
             const uint32_t n = tot[s];
             if (slot < 0 || n == 0) continue;
             const uint32_t tb = tbase[s];
-            uint8_t* g = static_cast<uint8_t*>(c.bufs[slot]) + tb;
+            uint8_t* g = static_cast<uint8_t*>(buf_ptr(c, slot)) + tb;
             const uint32_t so = m.out + adj[s] + tb;  // rv_smem offset of the region's first byte
             const uint32_t head = min(n, (16u - uint32_t(reinterpret_cast<uintptr_t>(g) & 15u)) & 15u);
             for (uint32_t i = lane; i < head; i += 32) g[i] = rv_smem[so + i];
@@ -257,7 +262,7 @@ __device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t,
 template <class W, bool GENERIC>
 __device__ __forceinline__ void emit_body(const DecodeParams& p, const int tile_id) {
     const Tile t = tile_of(p, tile_id);
-    const SmemMap m = smem_map(p.n_nodes, p.n_streams, p.smem_data_cap);
+    const SmemMap m = smem_map(p.n_nodes, p.n_streams, p.n_slots, p.smem_data_cap);
     const TileWindow w = stage_in<true>(p, t, tile_id, m);
     __syncthreads();
     if (w.staged) emit_walks<W, true>(p, t, tile_id, m, w);
