@@ -46,7 +46,17 @@ struct TileWindow {
     bool staged;
     int64_t t0, t1;   // byte range of the tile in `data`
     uint32_t mis;     // (data + t0) & 15: the window starts at the aligned-down address
+    int64_t o0, o1;   // this lane's record: byte range in `data`
+    int64_t f0, f1;   // (one lane) byte range of the tile `prefetch_dist` ahead, -1: none
 };
+
+// L2 prefetch: a CTA's first act is a dependent chain of DRAM round trips (offsets -> input window);
+// the CTA that ran `prefetch_dist` tiles earlier has already pulled those lines into L2.
+__device__ __forceinline__ void l2_prefetch_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+constexpr int kPrefetchLane = 32;  // the lane (first of warp 1) that carries the look-ahead
 
 // Loads the plan and the tile's byte window into shared memory.
 // EMIT: the lanes' cursors (tile base + in-tile prefix) and, further down, zeroing of the Utf8 staging
@@ -73,8 +83,27 @@ __device__ __forceinline__ TileWindow stage_in(const DecodeParams& p, const Tile
         for (int s = 0; s < p.n_streams; ++s) cur[s * kBlock + tid] = 0;
     }
     TileWindow w;
+    // One round trip: the tile's bounds, this lane's record bounds and (one lane) the bounds of the tile a
+    // later CTA will work on are all requested before anything waits.
     w.t0 = __ldg(p.offsets + t.r0);
     w.t1 = __ldg(p.offsets + t.r0 + t.nrec);
+    w.o0 = w.o1 = 0;
+    if (tid < t.nrec) {
+        w.o0 = __ldg(p.offsets + t.r0 + tid);
+        w.o1 = __ldg(p.offsets + t.r0 + tid + 1);
+    }
+    w.f0 = w.f1 = -1;
+    const int64_t ft = int64_t(tile_id) + p.prefetch_dist;
+    if (p.prefetch_dist > 0 && !p.tile_list && ft < p.n_tiles) {
+        const Tile f = tile_of(p, int(ft));
+        if (tid < 17 && f.r0 + 16 * tid <= p.n) l2_prefetch_line(p.offsets + f.r0 + 16 * tid);  // the 2 KiB (+8 B) of offsets of that tile
+        if (tid == kPrefetchLane) {
+            w.f0 = __ldg(p.offsets + f.r0);
+            w.f1 = __ldg(p.offsets + f.r0 + f.nrec);
+        }
+        if (EMIT && tid == kPrefetchLane + 1)
+            l2_prefetch_bulk(p.lane_off + size_t(ft) * p.n_streams * kBlock, uint32_t(p.n_streams) * kBlock * 4u);
+    }
     const int64_t span = w.t1 - w.t0;
     w.mis = uint32_t(reinterpret_cast<uintptr_t>(p.data + w.t0) & 15u);
     w.staged = span >= 0 && uint64_t(span) + w.mis <= uint64_t(p.smem_data_cap);
@@ -110,7 +139,7 @@ __device__ __forceinline__ int64_t init_ctx(C& c, const DecodeParams& p, const T
     c.pos = c.end = 0;
     const int64_t r = t.r0 + tid;
     if (c.in_range) {
-        const int64_t o0 = __ldg(p.offsets + r), o1 = __ldg(p.offsets + r + 1);
+        const int64_t o0 = w.o0, o1 = w.o1;
         if (o1 < o0 || o1 - o0 > int64_t(0xFFFFFFF0u)) c.err = E_OVERFLOW;  // malformed offsets / >4 GiB record
         else if (C::kShared) {
             if (o0 < w.t0 || o1 > w.t1) c.err = E_OVERFLOW;
@@ -125,6 +154,16 @@ __device__ __forceinline__ int64_t init_ctx(C& c, const DecodeParams& p, const T
 
 __device__ __forceinline__ void report(const DecodeParams& p, int64_t record, uint32_t code) {
     atomicMin(p.err, (static_cast<unsigned long long>(record) << 8) | code);
+}
+
+// The look-ahead lane asks L2 for the input window of the tile `prefetch_dist` ahead (its bounds arrived
+// long ago, with this tile's own offsets).
+__device__ __forceinline__ void prefetch_window(const DecodeParams& p, const TileWindow& w) {
+    if (threadIdx.x == kPrefetchLane && w.f0 >= 0 && w.f1 > w.f0 && w.f1 - w.f0 < (int64_t(1) << 20)) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p.data + w.f0) & ~uintptr_t(15);
+        const uintptr_t e = (reinterpret_cast<uintptr_t>(p.data + w.f1) + 15) & ~uintptr_t(15);
+        l2_prefetch_bulk(reinterpret_cast<const void*>(a), uint32_t(e - a));
+    }
 }
 
 // ---- count ----------------------------------------------------------------------------------
@@ -182,6 +221,7 @@ __device__ __forceinline__ void count_body(const DecodeParams& p, const int tile
     __syncthreads();
     uint32_t* lo = p.lane_off + size_t(tile_id) * p.n_streams * kBlock;
     for (int s = 0; s < p.n_streams; ++s) lo[s * kBlock + tid] = cur[s * kBlock + tid] + wtot[s * kWarps + warp];
+    prefetch_window(p, w);
 }
 
 // ---- emit -----------------------------------------------------------------------------------
@@ -237,6 +277,7 @@ __device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t,
     }
     c.stage_on = stage_on;
     W::template walk<WM_EMIT>(c, p.n_nodes);
+    prefetch_window(p, w);
 
     if (stage_on) {  // coalesced write-out of the staged Utf8 bytes, one warp per stream at a time
         __syncthreads();

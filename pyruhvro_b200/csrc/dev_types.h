@@ -116,6 +116,7 @@ struct DecodeParams {
     // ids) and the generic interpreter kernels are launched over that list (tile_list != nullptr).
     const int32_t* tile_list;  // interpreter pass over overflow tiles: blockIdx.x -> tile id
     int32_t* overflow;         // specialised count pass: list of tiles it skipped
+    int32_t prefetch_dist;    // CTAs resident on the device: a CTA prefetches (into L2) the tile that far ahead
     uint32_t smem_data_cap;   // bytes of shared memory for staging a tile's input bytes
     uint32_t smem_stage_cap;  // bytes of shared memory for staging a tile's Utf8 output bytes (emit)
 };

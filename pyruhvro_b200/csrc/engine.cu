@@ -449,6 +449,15 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         p.nodes = dp.nodes; p.n_nodes = int32_t(n_nodes_param); p.n_streams = S; p.n_slots = n_slots;
         p.sym_off = dp.sym_off; p.sym_bytes = dp.sym_bytes;
         p.smem_data_cap = uint32_t(cap_in);
+        p.prefetch_dist = 0;
+        if (!(std::getenv("RV_NO_PREFETCH") && std::getenv("RV_NO_PREFETCH")[0] == '1')) {
+            // CTAs resident on the device ~ how far ahead the tile a finishing CTA's successor will take is
+            const size_t per_cta = smem_count + 1024;
+            const int ctas_per_sm = int(std::max<size_t>(1, std::min<size_t>(8, (228 * 1024) / per_cta)));
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+            p.prefetch_dist = sms * ctas_per_sm;
+        }
         RV_CUDA(tile_agg.alloc(size_t(std::max(S, 1)) * size_t(n_tiles) * 4, stream));
         RV_CUDA(tile_base.alloc(size_t(std::max(S, 1)) * size_t(n_tiles) * 4, stream));
         RV_CUDA(lane_off.alloc(size_t(std::max(S, 1)) * size_t(n_tiles) * kBlock * 4, stream));
@@ -537,6 +546,11 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
             if (const char* ev_ = std::getenv("RV_NO_STAGE_OUT")) if (ev_[0] == '1') cap_out = 0;
             p.smem_stage_cap = uint32_t(cap_out);
             smem_emit = smem_count + cap_out;
+            if (p.prefetch_dist > 0) {
+                int sms = 148;
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+                p.prefetch_dist = sms * int(std::max<size_t>(1, std::min<size_t>(8, (228 * 1024) / (smem_emit + 1024))));
+            }
         }
         RV_CUDA(cudaEventRecord(ev[3], stream));
         if (use_jit) {
