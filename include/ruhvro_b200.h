@@ -109,6 +109,16 @@ rv_status rv_result_export_device(rv_result* r, int64_t batch, struct ArrowDevic
 
 void rv_result_free(rv_result* r);
 
+/* ---- multi-GPU: fix-ups for gathering shard-local batches into ONE RecordBatch -------------------------
+ * Records shard by message; each rank decodes its contiguous range (exactly the reference's per-chunk batches,
+ * deserialize.rs:57-68).  When a single batch is wanted the ranks all-gather every Arrow buffer (NCCL) and fix
+ * them up on the device with these two kernels (pyruhvro_b200/distributed.py drives it). */
+/* d_dst[i] = d_src[i] + add  — rebases a shard's i32 offsets by the totals of the shards before it. */
+rv_status rv_dev_rebase_i32(int32_t* d_dst, const int32_t* d_src, int64_t n, int32_t add, void* cuda_stream);
+/* ORs nbits bits of d_src_words (LSB-first) into d_dst_words starting at bit dst_bit; the destination must be
+ * zero-initialised (seam words are shared between shards).  Both pointers 4-byte aligned. */
+rv_status rv_dev_concat_bits(uint32_t* d_dst_words, int64_t dst_bit, const uint32_t* d_src_words, int64_t nbits, void* cuda_stream);
+
 /* ---- memory / introspection ------------------------------------------------------------- */
 
 void* rv_host_alloc(size_t bytes); /* pinned host memory (cudaHostAlloc); NULL on failure */

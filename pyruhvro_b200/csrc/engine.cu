@@ -954,6 +954,20 @@ int rv_last_timings(float* out_ms, int cap) {
     return n;
 }
 int rv_last_launch_count(void) { return t_launches; }
+rv_status rv_dev_rebase_i32(int32_t* d_dst, const int32_t* d_src, int64_t n, int32_t add, void* cuda_stream) {
+    if (n < 0 || (n > 0 && (!d_dst || !d_src))) return fail(RV_ERR_INVALID, "bad argument");
+    launch_rebase_i32(d_dst, d_src, n, add, static_cast<cudaStream_t>(cuda_stream));
+    RV_CUDA(cudaGetLastError());
+    return RV_OK;
+}
+
+rv_status rv_dev_concat_bits(uint32_t* d_dst_words, int64_t dst_bit, const uint32_t* d_src_words, int64_t nbits, void* cuda_stream) {
+    if (nbits < 0 || dst_bit < 0 || (nbits > 0 && (!d_dst_words || !d_src_words))) return fail(RV_ERR_INVALID, "bad argument");
+    launch_concat_bits(d_dst_words, dst_bit, d_src_words, nbits, static_cast<cudaStream_t>(cuda_stream));
+    RV_CUDA(cudaGetLastError());
+    return RV_OK;
+}
+
 const char* rv_last_walker(void) { return t_walker; }
 void rv_set_jit_enabled(int enabled) { g_jit_override.store(enabled < 0 ? -1 : (enabled ? 1 : 0)); }
 

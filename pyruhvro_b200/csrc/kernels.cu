@@ -13,6 +13,8 @@
 // Integer/byte work bounded by HBM bandwidth; no tensor-core use.
 #include "kernels.cuh"
 
+#include <algorithm>
+
 #include "dev_kernels.cuh"
 #include "interp.cuh"
 
@@ -107,7 +109,50 @@ __global__ void null_count_kernel(const NullCountJob* jobs, long long* ones_out)
     }
 }
 
+// ---- fix-ups for gathering shard-local Arrow buffers into one batch (multi-GPU) ----
+// dst[i] = src[i] + add: rebases a shard's i32 offsets by the total of the shards before it.
+__global__ void rebase_i32_kernel(int32_t* dst, const int32_t* src, long long n, int32_t add) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i] + add;
+}
+
+// ORs `nbits` bits of `src` (bit 0 first) into `dst` starting at bit `dst_bit`; dst must be zero where
+// nothing was written yet.  One thread per destination word; seam words are shared between shards, hence atomicOr.
+__global__ void concat_bits_kernel(uint32_t* dst, long long dst_bit, const uint32_t* src, long long nbits) {
+    const long long w0 = dst_bit >> 5, w1 = (dst_bit + nbits + 31) >> 5;
+    const unsigned sh = unsigned(dst_bit & 31);
+    const long long n_src_words = (nbits + 31) >> 5;
+    for (long long w = w0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; w < w1; w += (long long)gridDim.x * blockDim.x) {
+        const long long k = w - w0;  // source word whose low bits land at bit `sh` of this word
+        uint32_t lo = 0, hi = 0;
+        if (k < n_src_words) {
+            hi = src[k];
+            const long long rem = nbits - (k << 5);
+            if (rem < 32) hi &= (1u << rem) - 1u;
+        }
+        if (k >= 1 && sh) {
+            lo = src[k - 1];
+            const long long rem = nbits - ((k - 1) << 5);
+            if (rem < 32) lo &= (1u << rem) - 1u;
+        }
+        const uint32_t v = sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
+        if (v) atomicOr(dst + w, v);
+    }
+}
+
 }  // namespace
+
+void launch_rebase_i32(int32_t* dst, const int32_t* src, long long n, int32_t add, cudaStream_t s) {
+    if (n <= 0) return;
+    const int blocks = int(std::min<long long>((n + 255) / 256, 148 * 8));
+    rebase_i32_kernel<<<blocks, 256, 0, s>>>(dst, src, n, add);
+}
+
+void launch_concat_bits(uint32_t* dst, long long dst_bit, const uint32_t* src, long long nbits, cudaStream_t s) {
+    if (nbits <= 0) return;
+    const long long words = ((dst_bit + nbits + 31) >> 5) - (dst_bit >> 5);
+    const int blocks = int(std::min<long long>((words + 255) / 256, 148 * 8));
+    concat_bits_kernel<<<blocks, 256, 0, s>>>(dst, dst_bit, src, nbits);
+}
 
 cudaError_t prepare_kernels() {
     cudaError_t e = cudaFuncSetAttribute(count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
