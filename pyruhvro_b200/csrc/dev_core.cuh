@@ -38,7 +38,8 @@ struct WalkCtx {
     uint32_t pm;           // interpreter: presence by tree level
     uint64_t usel;         // interpreter: selected variant per union nesting level (8 bits each)
     const DNode* nodes;    // interpreter: the plan
-    uint32_t* cur;         // per-lane cursors: cur[stream * kBlock]
+    uint32_t* cur;         // interpreter: per-lane cursors in shared memory, cur[stream * kBlock]
+                           // (generated walkers keep their cursors in registers)
     void* const* bufs;     // slot -> buffer of this chunk (global memory table)
     uint32_t ptrs_soff;    // device emit: offset inside rv_smem of the CTA's copy of that table (0: none)
     const int32_t* sym_off;
@@ -313,8 +314,7 @@ RV_HD void copy_from_symbols(C& c, int slot_b, int stream, uint32_t o, const uin
 }
 
 template <int MODE, int D, class C>
-RV_HD void utf8_finish(C& c, bool valid, uint32_t len, int slot_a, int slot_v, int stream, uint32_t row) {
-    uint32_t& cur = c.cur[uint32_t(stream) * kBlock];
+RV_HD void utf8_finish(C& c, bool valid, uint32_t len, int slot_a, int slot_v, uint32_t& cur, uint32_t row) {
     if (MODE == WM_COUNT) {
         const uint32_t nxt = cur + len;
         if (nxt < cur) fail(c, E_OVERFLOW);
@@ -328,20 +328,20 @@ RV_HD void utf8_finish(C& c, bool valid, uint32_t len, int slot_a, int slot_v, i
 }
 
 template <int MODE, int D, class C>
-RV_HD void op_str(C& c, bool valid, int slot_a, int slot_b, int slot_v, int stream, uint32_t row) {  // read_string :902-922
+RV_HD void op_str(C& c, bool valid, int slot_a, int slot_b, int slot_v, int stream, uint32_t row, uint32_t& cur) {  // read_string :902-922
     uint32_t len = 0;
     if (valid) {
         if (!rd_len<MODE == WM_COUNT>(c, len)) { valid = false; len = 0; }
         else {
-            if (MODE == WM_EMIT && len) copy_from_record(c, slot_b, stream, c.cur[uint32_t(stream) * kBlock], c.pos, len);
+            if (MODE == WM_EMIT && len) copy_from_record(c, slot_b, stream, cur, c.pos, len);
             c.pos += len;
         }
     }
-    utf8_finish<MODE, D>(c, valid, len, slot_a, slot_v, stream, row);
+    utf8_finish<MODE, D>(c, valid, len, slot_a, slot_v, cur, row);
 }
 
 template <int MODE, int D, class C>
-RV_HD void op_enum(C& c, bool valid, int slot_a, int slot_b, int slot_v, int stream, uint32_t row, int sym_base, int n_sym) {  // append_enum :570-578
+RV_HD void op_enum(C& c, bool valid, int slot_a, int slot_b, int slot_v, int stream, uint32_t row, int sym_base, int n_sym, uint32_t& cur) {  // append_enum :570-578
     uint32_t len = 0;
     if (valid) {
         const int64_t l = rd_varint<MODE == WM_COUNT>(c);
@@ -350,10 +350,10 @@ RV_HD void op_enum(C& c, bool valid, int slot_a, int slot_b, int slot_v, int str
         else {
             const int32_t b0 = c.sym_off[sym_base + int32_t(l)];
             len = uint32_t(c.sym_off[sym_base + int32_t(l) + 1] - b0);
-            if (MODE == WM_EMIT) copy_from_symbols(c, slot_b, stream, c.cur[uint32_t(stream) * kBlock], c.sym_bytes + b0, len);
+            if (MODE == WM_EMIT) copy_from_symbols(c, slot_b, stream, cur, c.sym_bytes + b0, len);
         }
     }
-    utf8_finish<MODE, D>(c, valid, len, slot_a, slot_v, stream, row);
+    utf8_finish<MODE, D>(c, valid, len, slot_a, slot_v, cur, row);
 }
 
 // ---- containers -------------------------------------------------------------------------------
@@ -398,8 +398,7 @@ RV_HD int rd_block(C& c, int64_t& rem, uint32_t& total, bool zero_items) {
 }
 
 template <int MODE, int D, class C>
-RV_HD void list_finish(C& c, bool valid, uint32_t first_row, uint32_t total, int slot_a, int slot_v, int stream, uint32_t row) {
-    uint32_t& cur = c.cur[uint32_t(stream) * kBlock];
+RV_HD void list_finish(C& c, bool valid, uint32_t first_row, uint32_t total, int slot_a, int slot_v, uint32_t& cur, uint32_t row) {
     if (MODE == WM_COUNT) {
         const uint32_t nxt = cur + total;
         if (nxt < cur || nxt > 0x7FFFFFFFu) fail(c, E_OVERFLOW);

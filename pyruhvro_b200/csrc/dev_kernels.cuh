@@ -10,7 +10,8 @@
 //               values / offsets are stored row-aligned; space-0 validity is one ballot word per warp.
 //
 // Shared-memory map (dynamic, rv_smem):
-//   [nodes n_nodes*32][cur S*256*4][wtot S*8*4 (emit: tile bases)][tot (S+1)*4][adj S*4][ptrs n_slots*8][in: smem_data_cap][out: smem_stage_cap]
+//   [nodes n_nodes*32][wtot S*8*4 (emit: tile bases)][tot (S+1)*4][adj S*4][ptrs n_slots*8][cur S*256*4][in: smem_data_cap][out: smem_stage_cap]
+//   (register-cursor walkers: `cur` overlays `in`)
 #pragma once
 #include "dev_core.cuh"
 
@@ -61,8 +62,8 @@ constexpr int kPrefetchLane = 32;  // the lane (first of warp 1) that carries th
 // Loads the plan and the tile's byte window into shared memory.
 // EMIT: the lanes' cursors (tile base + in-tile prefix) and, further down, zeroing of the Utf8 staging
 // area are issued here too, so their latency overlaps the input loads.
-template <bool EMIT>
-__device__ __forceinline__ TileWindow stage_in(const DecodeParams& p, const Tile& t, const int tile_id, const SmemMap& m) {
+template <bool EMIT, class W>
+__device__ __forceinline__ TileWindow stage_in(const DecodeParams& p, const Tile& t, const int tile_id, const SmemMap& m, typename W::Cur& q) {
     const int tid = threadIdx.x;
     if (p.n_nodes) {
         uint4* dn = reinterpret_cast<uint4*>(rv_smem + m.nodes);
@@ -75,13 +76,20 @@ __device__ __forceinline__ TileWindow stage_in(const DecodeParams& p, const Tile
         void* const* gp = p.bufs + size_t(t.chunk) * p.n_slots;
         for (int i = tid; i < p.n_slots; i += kBlock) sp[i] = gp[i];
         const uint32_t* lo = p.lane_off + size_t(tile_id) * p.n_streams * kBlock;
-        for (int s = 0; s < p.n_streams; ++s)
-            cur[s * kBlock + tid] = __ldg(lo + s * kBlock + tid) + __ldg(p.tile_base + size_t(s) * p.n_tiles + tile_id);
+        if constexpr (W::kRegCursors) {
+#pragma unroll
+            for (int s = 0; s < W::kStreams; ++s)
+                q.v[s] = __ldg(lo + s * kBlock + tid) + __ldg(p.tile_base + size_t(s) * p.n_tiles + tile_id);
+        } else {
+            for (int s = 0; s < p.n_streams; ++s)
+                cur[s * kBlock + tid] = __ldg(lo + s * kBlock + tid) + __ldg(p.tile_base + size_t(s) * p.n_tiles + tile_id);
+        }
         uint4* z = reinterpret_cast<uint4*>(rv_smem + m.out);
         for (uint32_t i = tid; i < (p.smem_stage_cap >> 4); i += kBlock) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    } else {
+    } else if constexpr (!W::kRegCursors) {
         for (int s = 0; s < p.n_streams; ++s) cur[s * kBlock + tid] = 0;
     }
+    (void)cur;
     TileWindow w;
     // One round trip: the tile's bounds, this lane's record bounds and (one lane) the bounds of the tile a
     // later CTA will work on are all requested before anything waits.
@@ -168,10 +176,14 @@ __device__ __forceinline__ void prefetch_window(const DecodeParams& p, const Til
 
 // ---- count ----------------------------------------------------------------------------------
 template <class W, bool SM>
-__device__ __forceinline__ void count_walk(const DecodeParams& p, const Tile& t, const SmemMap& m, const TileWindow& w) {
+__device__ __forceinline__ void count_walk(const DecodeParams& p, const Tile& t, const SmemMap& m, const TileWindow& w, typename W::Cur& q) {
     WalkCtx<SM> c;
     const int64_t r = init_ctx(c, p, t, m, w);
-    W::template walk<WM_COUNT>(c, p.n_nodes);
+    if constexpr (W::kRegCursors) {
+#pragma unroll
+        for (int s = 0; s < W::kStreams; ++s) q.v[s] = 0;
+    }
+    W::template walk<WM_COUNT>(c, p.n_nodes, q);
     if (c.in_range && c.err) report(p, r, c.err);
 }
 
@@ -181,11 +193,12 @@ __device__ __forceinline__ void count_walk(const DecodeParams& p, const Tile& t,
 template <class W, bool GENERIC>
 __device__ __forceinline__ void count_body(const DecodeParams& p, const int tile_id) {
     const Tile t = tile_of(p, tile_id);
-    const SmemMap m = smem_map(p.n_nodes, p.n_streams, p.n_slots, p.smem_data_cap);
-    const TileWindow w = stage_in<false>(p, t, tile_id, m);
+    const SmemMap m = smem_map(p.n_nodes, p.n_streams, p.n_slots, p.smem_data_cap, W::kRegCursors);
+    typename W::Cur q;
+    const TileWindow w = stage_in<false, W>(p, t, tile_id, m, q);
     __syncthreads();
-    if (w.staged) count_walk<W, true>(p, t, m, w);
-    else if constexpr (GENERIC) count_walk<W, false>(p, t, m, w);
+    if (w.staged) count_walk<W, true>(p, t, m, w, q);
+    else if constexpr (GENERIC) count_walk<W, false>(p, t, m, w, q);
     else {
         if (threadIdx.x == 0) p.overflow[1 + atomicAdd(p.overflow, 1)] = tile_id;
         return;  // uniform: the whole CTA leaves
@@ -196,6 +209,10 @@ __device__ __forceinline__ void count_body(const DecodeParams& p, const int tile
     uint32_t* cur = reinterpret_cast<uint32_t*>(rv_smem + m.cur);
     uint32_t* wtot = reinterpret_cast<uint32_t*>(rv_smem + m.wtot);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if constexpr (W::kRegCursors) {  // the scan area overlays the (now dead) input window
+#pragma unroll
+        for (int s = 0; s < W::kStreams; ++s) cur[s * kBlock + tid] = q.v[s];
+    }
     for (int s = 0; s < p.n_streams; ++s) {
         const uint32_t v = cur[s * kBlock + tid];
         uint32_t incl = v;
@@ -226,7 +243,7 @@ __device__ __forceinline__ void count_body(const DecodeParams& p, const int tile
 
 // ---- emit -----------------------------------------------------------------------------------
 template <class W, bool SM>
-__device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t, const int tile_id, const SmemMap& m, const TileWindow& w) {
+__device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t, const int tile_id, const SmemMap& m, const TileWindow& w, typename W::Cur& q) {
     WalkCtx<SM> c;
     (void)init_ctx(c, p, t, m, w);
     uint32_t* tbase = reinterpret_cast<uint32_t*>(rv_smem + m.wtot);  // reused: [S] tile bases, then [S] region alignments
@@ -276,7 +293,7 @@ __device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t,
         }
     }
     c.stage_on = stage_on;
-    W::template walk<WM_EMIT>(c, p.n_nodes);
+    W::template walk<WM_EMIT>(c, p.n_nodes, q);
     prefetch_window(p, w);
 
     if (stage_on) {  // coalesced write-out of the staged Utf8 bytes, one warp per stream at a time
@@ -303,11 +320,12 @@ __device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t,
 template <class W, bool GENERIC>
 __device__ __forceinline__ void emit_body(const DecodeParams& p, const int tile_id) {
     const Tile t = tile_of(p, tile_id);
-    const SmemMap m = smem_map(p.n_nodes, p.n_streams, p.n_slots, p.smem_data_cap);
-    const TileWindow w = stage_in<true>(p, t, tile_id, m);
+    const SmemMap m = smem_map(p.n_nodes, p.n_streams, p.n_slots, p.smem_data_cap, W::kRegCursors);
+    typename W::Cur q;
+    const TileWindow w = stage_in<true, W>(p, t, tile_id, m, q);
     __syncthreads();
-    if (w.staged) emit_walks<W, true>(p, t, tile_id, m, w);
-    else if constexpr (GENERIC) emit_walks<W, false>(p, t, tile_id, m, w);
+    if (w.staged) emit_walks<W, true>(p, t, tile_id, m, w, q);
+    else if constexpr (GENERIC) emit_walks<W, false>(p, t, tile_id, m, w, q);
     // else: the tile is on the overflow list and the interpreter pass emits it
 }
 

@@ -122,24 +122,33 @@ struct DecodeParams {
 };
 
 // Dynamic shared-memory map of count/emit CTAs (byte offsets inside the CTA's shared memory):
-//   [nodes n_nodes*32][cur S*256*4][wtot S*8*4][tot (S+1)*4][adj S*4][ptrs n_slots*8][in: data_cap][out: stage_cap]
+//   [nodes n_nodes*32][wtot S*8*4][tot (S+1)*4][adj S*4][ptrs n_slots*8][cur S*256*4][in: data_cap][out: stage_cap]
+// alias_cur (walkers that keep their cursors in registers): the scan area `cur` overlays the input window
+// (it is only written after every lane finished reading the window) and costs no extra shared memory.
 struct SmemMap {
-    uint32_t nodes, cur, wtot, tot, adj, ptrs, in, out;
+    uint32_t nodes, wtot, tot, adj, ptrs, cur, in, out;
 };
 
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-inline SmemMap smem_map(int n_nodes, int n_streams, int n_slots, uint32_t data_cap) {
+inline SmemMap smem_map(int n_nodes, int n_streams, int n_slots, uint32_t data_cap, bool alias_cur) {
     SmemMap m;
     m.nodes = 0;
-    m.cur = uint32_t(n_nodes) * 32u;
-    m.wtot = m.cur + uint32_t(n_streams) * kBlock * 4u;
+    m.wtot = uint32_t(n_nodes) * 32u;
     m.tot = m.wtot + uint32_t(n_streams) * kWarps * 4u;
     m.adj = m.tot + uint32_t(n_streams + 1) * 4u;
     m.ptrs = (m.adj + uint32_t(n_streams) * 4u + 15u) & ~15u;
-    m.in = (m.ptrs + uint32_t(n_slots) * 8u + 15u) & ~15u;
-    m.out = (m.in + data_cap + 15u) & ~15u;
+    m.cur = (m.ptrs + uint32_t(n_slots) * 8u + 15u) & ~15u;
+    const uint32_t cur_bytes = uint32_t(n_streams) * kBlock * 4u;
+    if (alias_cur) {
+        m.in = m.cur;
+        const uint32_t win = data_cap > cur_bytes ? data_cap : cur_bytes;
+        m.out = (m.in + win + 15u) & ~15u;
+    } else {
+        m.in = (m.cur + cur_bytes + 15u) & ~15u;
+        m.out = (m.in + data_cap + 15u) & ~15u;
+    }
     return m;
 }
 

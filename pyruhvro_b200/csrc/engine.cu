@@ -429,18 +429,19 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         const int plan_nodes = use_jit ? 0 : int(plan.nodes.size());  // the generated walker has the plan baked in
         // shared-memory budget: [plan +] cursors are fixed; then the tile's input bytes; then (emit) the
         // staging area in which the tile's Utf8 output is assembled for coalesced write-out
-        const size_t fixed = smem_map(plan_nodes, S, n_slots, 0).in;
+        const size_t fixed = smem_map(plan_nodes, S, n_slots, 0, use_jit).in;
         const size_t limit = 227 * 1024;
         if (fixed + 2048 > limit) return fail(RV_ERR_SCHEMA, "schema too wide for the shared-memory cursor table");
         const double avg = total_bytes > 0 ? double(total_bytes) / double(n) : 16.0;
         // a tile is the sum of 256 record sizes: its spread is a few percent, so a 12% margin keeps almost
         // every tile in shared memory while letting three CTAs share an SM on the Kafka-shaped workloads
-        size_t want = size_t(avg * kBlock * 1.12) + 768;
+        size_t want = size_t(avg * kBlock * 1.10) + 512;
+        if (use_jit) want = std::max<size_t>(want, size_t(S) * kBlock * 4);  // the scan area overlays the window
         want = (want + 255) & ~size_t(255);
         want = std::max<size_t>(want, 4096);
         const size_t room = (limit - fixed - 64) & ~size_t(15);
         size_t cap_in = std::min(want, room);
-        smem_count = smem_map(plan_nodes, S, n_slots, uint32_t(cap_in)).out;
+        smem_count = smem_map(plan_nodes, S, n_slots, uint32_t(cap_in), use_jit).out;
         smem_room_out = room > cap_in ? room - cap_in : 0;
         p.stream_slot = dp.stream_slot;
         const int n_nodes_param = plan_nodes;
@@ -483,8 +484,8 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
             pi.n_nodes = int32_t(plan.nodes.size());
             pi.tile_list = static_cast<const int32_t*>(d_overflow.p) + 1;
             pi.smem_stage_cap = 0;
-            pi.smem_data_cap = uint32_t(std::min<size_t>(cap_in, (limit - smem_map(pi.n_nodes, S, n_slots, 0).in - 64) & ~size_t(15)));
-            smem_interp = smem_map(pi.n_nodes, S, n_slots, pi.smem_data_cap).out;
+            pi.smem_data_cap = uint32_t(std::min<size_t>(cap_in, (limit - smem_map(pi.n_nodes, S, n_slots, 0, false).in - 64) & ~size_t(15)));
+            smem_interp = smem_map(pi.n_nodes, S, n_slots, pi.smem_data_cap, false).out;
             launch_count(pi, kOverflowGrid, smem_interp, stream);
             t_launches += 1;
         } else {

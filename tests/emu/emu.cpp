@@ -46,6 +46,16 @@ std::vector<Tile> make_tiles(int64_t n, int k) {
 
 using Ctx = WalkCtx<false>;
 
+// register-cursor walkers exchange their cursors with the emulation's cur[stream][lane] table
+template <class Q>
+void store_cursors(const Q& q, uint32_t* cur_lane, int S) {
+    if constexpr (EmuWalker::kRegCursors) for (int s = 0; s < S; ++s) cur_lane[size_t(s) * kTile] = q.v[s];
+}
+template <class Q>
+void load_cursors(Q& q, const uint32_t* cur_lane, int S) {
+    if constexpr (EmuWalker::kRegCursors) for (int s = 0; s < S; ++s) q.v[s] = cur_lane[size_t(s) * kTile];
+}
+
 void init_ctx(Ctx& c, const Plan& plan, const uint8_t* data, const int64_t* off, const Tile& t, int lane,
               uint32_t* cur, int S, void* const* bufs) {
     std::memset(&c, 0, sizeof c);
@@ -92,7 +102,9 @@ int emu_decode(const char* json, size_t len, const uint8_t* data, const int64_t*
             for (int lane = 0; lane < kTile; ++lane) {
                 Ctx c;
                 init_ctx(c, plan, data, off, tiles[ti], lane, cur.data(), S, nullptr);
-                EmuWalker::walk<WM_COUNT>(c, int(plan.nodes.size()));
+                EmuWalker::Cur q{};
+                EmuWalker::walk<WM_COUNT>(c, int(plan.nodes.size()), q);
+                store_cursors(q, cur.data() + lane, S);
                 if (c.in_range && c.err) { *err_record = tiles[ti].r0 + lane; return int(c.err); }
             }
             for (int s = 0; s < S; ++s) {
@@ -132,7 +144,9 @@ int emu_decode(const char* json, size_t len, const uint8_t* data, const int64_t*
             for (int lane = 0; lane < kTile; ++lane) {
                 Ctx c;
                 init_ctx(c, plan, data, off, t, lane, cur.data(), S, nullptr);
-                EmuWalker::walk<WM_COUNT>(c, int(plan.nodes.size()));
+                EmuWalker::Cur q{};
+                EmuWalker::walk<WM_COUNT>(c, int(plan.nodes.size()), q);
+                store_cursors(q, cur.data() + lane, S);
             }
             for (int s = 0; s < S; ++s) {  // exclusive scan across lanes + tile base
                 uint32_t run = tile_base[ti][size_t(s)];
@@ -144,7 +158,9 @@ int emu_decode(const char* json, size_t len, const uint8_t* data, const int64_t*
             for (int lane = 0; lane < kTile; ++lane) {
                 Ctx c;
                 init_ctx(c, plan, data, off, t, lane, cur.data(), S, cb);
-                EmuWalker::walk<WM_EMIT>(c, int(plan.nodes.size()));
+                EmuWalker::Cur q{};
+                load_cursors(q, cur.data() + lane, S);
+                EmuWalker::walk<WM_EMIT>(c, int(plan.nodes.size()), q);
             }
         }
         // ---- null counts ----
