@@ -230,6 +230,7 @@ def main():
         h = step_device()
         arrow_bytes, buffer_bytes = L.rv_result_arrow_bytes(h), L.rv_result_buffer_bytes(h)
         L.rv_result_free(h)
+    overflow_tiles = 0
     kt = np.zeros(6, dtype=np.float64)
     tbuf = (ctypes.c_float * 6)()
     launches = 0
@@ -243,6 +244,7 @@ def main():
         L.rv_last_timings(tbuf, 6)
         kt += np.frombuffer(tbuf, dtype=np.float32)
         launches += L.rv_last_launch_count()
+        overflow_tiles = L.rv_last_overflow_tiles()
         L.rv_result_free(h)
     e1.record(stream)
     torch.cuda.synchronize()
@@ -321,7 +323,8 @@ def main():
                      "frac": emit_gbs / peak, "traffic": traffic, "algorithmic_bytes": emit_bytes, "kernel_ms": kt[2],
                      "peak_source": peak_src,
                      "count_kernel": {"achieved": count_gbs, "frac": count_gbs / peak, "algorithmic_bytes": count_bytes, "kernel_ms": kt[0]},
-                     "scan_kernel_ms": kt[1], "null_count_kernel_ms": kt[3]},
+                     "scan_kernel_ms": kt[1], "null_count_kernel_ms": kt[3], "walker": pr.last_walker(),
+                     "overflow_tiles_per_step": overflow_tiles},
         "clocks": sampler.summary(),
     }
     if cpu is not None:

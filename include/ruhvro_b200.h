@@ -135,6 +135,9 @@ int rv_last_launch_count(void);
  * with NVRTC for the device's architecture) or "interp" (the statically compiled generic kernels).
  * Both are GPU paths; RV_JIT=0 in the environment forces "interp". */
 const char* rv_last_walker(void);
+/* Tiles of the last decode on this thread that did not fit the shared-memory window of the specialised
+ * kernels and were handled by the interpreter overflow pass (diagnostics). */
+long long rv_last_overflow_tiles(void);
 /* 1 / 0: use / do not use the schema-specialised kernels from now on; -1: follow the RV_JIT environment variable. */
 void rv_set_jit_enabled(int enabled);
 

@@ -37,6 +37,12 @@ thread_local std::string t_error;
 thread_local float t_timings[6] = {0, 0, 0, 0, 0, 0};
 thread_local int t_launches = 0;
 thread_local const char* t_walker = "none";
+thread_local long long t_overflow_tiles = 0;
+
+double env_double(const char* name, double dflt) {
+    const char* v = std::getenv(name);
+    return v && *v ? std::atof(v) : dflt;
+}
 
 rv_status fail(rv_status st, const std::string& msg) {
     t_error = msg;
@@ -319,6 +325,9 @@ const JitState& ensure_jit(rv_schema* s, int device) {
     if (e == cudaSuccess) e = cudaLibraryGetKernel(&j.emit, j.lib, "rvj_emit");
     if (e == cudaSuccess) e = cudaFuncSetAttribute(reinterpret_cast<const void*>(j.count), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(reinterpret_cast<const void*>(j.emit), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    // occupancy is bounded by shared memory: ask for the largest carveout instead of the driver's guess
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(reinterpret_cast<const void*>(j.count), cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(reinterpret_cast<const void*>(j.emit), cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) { j.status = std::string("loading the compiled walker failed: ") + cudaGetErrorString(e); (void)cudaGetLastError(); return j; }
     j.ok = true;
     j.status = "ok";
@@ -393,13 +402,14 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
 
     std::vector<unsigned long long> chunk_tot(size_t(k) * size_t(std::max(S, 1)), 0ull);
     DecodeParams p{};
-    DevBuf tile_agg, tile_base, lane_off, d_chunk_tot, d_err, d_bufs, d_overflow;
+    DevBuf tile_agg, tile_base, lane_off, d_chunk_tot, d_err, d_bufs, d_overflow, d_stats;
     DecodeParams pi{};   // interpreter pass over the tiles the specialised kernels skipped
     size_t smem_interp = 0;
     cudaEvent_t ev[8];
     for (auto& e : ev) RV_CUDA(cudaEventCreate(&e));
     struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 8; ++i) cudaEventDestroy(e[i]); } } evg{ev};
     size_t smem_count = 0, smem_emit = 0, smem_room_out = 0;
+    unsigned long long max_utf8 = 0;
     bool use_jit = false;
     cudaKernel_t jit_count = nullptr, jit_emit = nullptr;
 
@@ -412,13 +422,25 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         const int64_t n_tiles = tpc * (k - 1) + tiles_last;
         if (n_tiles > 0x7FFFFFF0ll) return fail(RV_ERR_INVALID, "too many records for one call");
 
+        // tiling is known: fill it in first so the sizing kernel can use it
+        p.data = d_data; p.offsets = d_offsets; p.n = n; p.chunk_rows = chunk_rows; p.k = k;
+        p.tiles_per_chunk = int32_t(tpc); p.n_tiles = int32_t(n_tiles);
+        RV_CUDA(d_stats.alloc(16, stream));
+        RV_CUDA(cudaMemsetAsync(d_stats.p, 0, 16, stream));
+        launch_tile_span_max(p, static_cast<unsigned long long*>(d_stats.p), stream);
+        RV_CUDA(cudaGetLastError());
+        t_launches += 1;
+        unsigned long long max_span = 0;
         int64_t total_bytes = total_bytes_hint;
-        if (total_bytes < 0) {
-            int64_t ends[2];
-            RV_CUDA(cudaMemcpyAsync(&ends[0], d_offsets, 8, cudaMemcpyDeviceToHost, stream));
-            RV_CUDA(cudaMemcpyAsync(&ends[1], d_offsets + n, 8, cudaMemcpyDeviceToHost, stream));
+        {
+            int64_t ends[2] = {0, 0};
+            RV_CUDA(cudaMemcpyAsync(&max_span, d_stats.p, 8, cudaMemcpyDeviceToHost, stream));
+            if (total_bytes < 0) {
+                RV_CUDA(cudaMemcpyAsync(&ends[0], d_offsets, 8, cudaMemcpyDeviceToHost, stream));
+                RV_CUDA(cudaMemcpyAsync(&ends[1], d_offsets + n, 8, cudaMemcpyDeviceToHost, stream));
+            }
             RV_CUDA(cudaStreamSynchronize(stream));
-            total_bytes = ends[1] - ends[0];
+            if (total_bytes < 0) total_bytes = ends[1] - ends[0];
         }
         // Walker: schema-specialised (NVRTC) when available, else the generic interpreter.
         const JitState& jit = ensure_jit(s, device);
@@ -433,20 +455,18 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         const size_t limit = 227 * 1024;
         if (fixed + 2048 > limit) return fail(RV_ERR_SCHEMA, "schema too wide for the shared-memory cursor table");
         const double avg = total_bytes > 0 ? double(total_bytes) / double(n) : 16.0;
-        // a tile is the sum of 256 record sizes: its spread is a few percent, so a 12% margin keeps almost
-        // every tile in shared memory while letting three CTAs share an SM on the Kafka-shaped workloads
-        size_t want = size_t(avg * kBlock * 1.10) + 512;
+        // The window is sized for the LARGEST tile (measured above), so no tile needs the interpreter overflow
+        // pass; outliers beyond 1.5x the mean tile are not allowed to shrink everyone's occupancy and do take it.
+        size_t want = std::min<size_t>(size_t(max_span), size_t(avg * kBlock * env_double("RV_IN_CLAMP", 1.5))) + 48;
         if (use_jit) want = std::max<size_t>(want, size_t(S) * kBlock * 4);  // the scan area overlays the window
-        want = (want + 255) & ~size_t(255);
-        want = std::max<size_t>(want, 4096);
+        want = (want + 63) & ~size_t(63);
+        want = std::max<size_t>(want, 2048);
         const size_t room = (limit - fixed - 64) & ~size_t(15);
         size_t cap_in = std::min(want, room);
         smem_count = smem_map(plan_nodes, S, n_slots, uint32_t(cap_in), use_jit).out;
         smem_room_out = room > cap_in ? room - cap_in : 0;
         p.stream_slot = dp.stream_slot;
         const int n_nodes_param = plan_nodes;
-        p.data = d_data; p.offsets = d_offsets; p.n = n; p.chunk_rows = chunk_rows; p.k = k;
-        p.tiles_per_chunk = int32_t(tpc); p.n_tiles = int32_t(n_tiles);
         p.nodes = dp.nodes; p.n_nodes = int32_t(n_nodes_param); p.n_streams = S; p.n_slots = n_slots;
         p.sym_off = dp.sym_off; p.sym_bytes = dp.sym_bytes;
         p.smem_data_cap = uint32_t(cap_in);
@@ -494,13 +514,19 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         RV_CUDA(cudaEventRecord(ev[1], stream));
         launch_scan(p, stream);
         RV_CUDA(cudaEventRecord(ev[2], stream));
+        launch_tile_utf8_max(p, static_cast<unsigned long long*>(d_stats.p) + 1, stream);
+        t_launches += 1;
         RV_CUDA(cudaGetLastError());
         t_launches += S > 0 ? 2 : 1;
 
         unsigned long long err_word = ~0ull;
+        int overflow_n = 0;
+        RV_CUDA(cudaMemcpyAsync(&overflow_n, d_overflow.p, 4, cudaMemcpyDeviceToHost, stream));
         RV_CUDA(cudaMemcpyAsync(&err_word, d_err.p, 8, cudaMemcpyDeviceToHost, stream));
+        RV_CUDA(cudaMemcpyAsync(&max_utf8, static_cast<unsigned long long*>(d_stats.p) + 1, 8, cudaMemcpyDeviceToHost, stream));
         if (S > 0) RV_CUDA(cudaMemcpyAsync(chunk_tot.data(), d_chunk_tot.p, chunk_tot.size() * 8, cudaMemcpyDeviceToHost, stream));
         RV_CUDA(cudaStreamSynchronize(stream));
+        t_overflow_tiles = overflow_n;
         if (err_word != ~0ull) {
             const uint32_t code = uint32_t(err_word & 0xFF);
             return fail(rv_status(code), std::string(err_text(code)) + " (record " + std::to_string(int64_t(err_word >> 8) + record_base) + ")");
@@ -539,8 +565,11 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
             }
             size_t cap_out = 0;
             if (n_utf8 > 0) {
-                cap_out = size_t(double(utf8) / double(p.n_tiles) * 1.12) + size_t(n_utf8) * 32 + 512;
-                cap_out = (cap_out + 255) & ~size_t(255);
+                const double per_tile = double(utf8) / double(p.n_tiles);
+                // the largest tile's Utf8 bytes (measured), clamped at 1.5x the mean for outliers: a tile that
+                // outgrows the staging area writes its strings straight to global memory
+                cap_out = std::min<size_t>(size_t(max_utf8), size_t(per_tile * env_double("RV_OUT_CLAMP", 1.5)) + size_t(n_utf8) * 31) + 64;
+                cap_out = (cap_out + 63) & ~size_t(63);
                 if (cap_out > smem_room_out) cap_out = smem_room_out & ~size_t(15);
                 if (cap_out < 1024) cap_out = 0;
             }
@@ -970,6 +999,7 @@ rv_status rv_dev_concat_bits(uint32_t* d_dst_words, int64_t dst_bit, const uint3
 }
 
 const char* rv_last_walker(void) { return t_walker; }
+long long rv_last_overflow_tiles(void) { return t_overflow_tiles; }
 void rv_set_jit_enabled(int enabled) { g_jit_override.store(enabled < 0 ? -1 : (enabled ? 1 : 0)); }
 
 int64_t rv_schema_walker_source(const rv_schema* s, char* buf, size_t cap) {

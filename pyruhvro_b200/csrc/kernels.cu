@@ -109,6 +109,32 @@ __global__ void null_count_kernel(const NullCountJob* jobs, long long* ones_out)
     }
 }
 
+// ---- window sizing: the largest tile decides how much shared memory a CTA needs ---------------------
+// max over tiles of the tile's input byte span (one thread per tile).
+__global__ void tile_span_max_kernel(const DecodeParams p, unsigned long long* out_max) {
+    unsigned long long m = 0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < p.n_tiles; t += gridDim.x * blockDim.x) {
+        const Tile tl = tile_of(p, t);
+        const long long span = p.offsets[tl.r0 + tl.nrec] - p.offsets[tl.r0];
+        if (span > 0 && (unsigned long long)span > m) m = (unsigned long long)span;
+    }
+    for (int d = 16; d; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, m, d); if (o > m) m = o; }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out_max, m);
+}
+
+// max over tiles of the Utf8 bytes the tile stages for write-out (sum over byte streams, + alignment slack).
+__global__ void tile_utf8_max_kernel(const DecodeParams p, unsigned long long* out_max) {
+    unsigned long long m = 0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < p.n_tiles; t += gridDim.x * blockDim.x) {
+        unsigned long long sum = 0;
+        for (int s = 0; s < p.n_streams; ++s)
+            if (p.stream_slot[s] >= 0) sum += p.tile_agg[size_t(s) * p.n_tiles + t] + 31ull;
+        if (sum > m) m = sum;
+    }
+    for (int d = 16; d; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, m, d); if (o > m) m = o; }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out_max, m);
+}
+
 // ---- fix-ups for gathering shard-local Arrow buffers into one batch (multi-GPU) ----
 // dst[i] = src[i] + add: rebases a shard's i32 offsets by the total of the shards before it.
 __global__ void rebase_i32_kernel(int32_t* dst, const int32_t* src, long long n, int32_t add) {
@@ -141,6 +167,16 @@ __global__ void concat_bits_kernel(uint32_t* dst, long long dst_bit, const uint3
 
 }  // namespace
 
+void launch_tile_span_max(const DecodeParams& p, unsigned long long* out_max, cudaStream_t s) {
+    const int blocks = std::max(1, std::min((p.n_tiles + 255) / 256, 148 * 4));
+    tile_span_max_kernel<<<blocks, 256, 0, s>>>(p, out_max);
+}
+
+void launch_tile_utf8_max(const DecodeParams& p, unsigned long long* out_max, cudaStream_t s) {
+    const int blocks = std::max(1, std::min((p.n_tiles + 255) / 256, 148 * 4));
+    tile_utf8_max_kernel<<<blocks, 256, 0, s>>>(p, out_max);
+}
+
 void launch_rebase_i32(int32_t* dst, const int32_t* src, long long n, int32_t add, cudaStream_t s) {
     if (n <= 0) return;
     const int blocks = int(std::min<long long>((n + 255) / 256, 148 * 8));
@@ -156,8 +192,10 @@ void launch_concat_bits(uint32_t* dst, long long dst_bit, const uint32_t* src, l
 
 cudaError_t prepare_kernels() {
     cudaError_t e = cudaFuncSetAttribute(count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(count_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(emit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    return e;
 }
 
 void launch_count(const DecodeParams& p, int n_ctas, size_t smem, cudaStream_t s) {
