@@ -34,6 +34,7 @@ struct ArrowDeviceArray; /* Arrow C Device Data Interface */
 
 typedef struct rv_schema rv_schema; /* parsed Avro schema + decode plan; immutable, ref-counted */
 typedef struct rv_result rv_result; /* the k RecordBatches of one decode call */
+typedef struct rv_encoded rv_encoded; /* the k Binary arrays of one encode call */
 
 typedef enum rv_status {
     RV_OK = 0,
@@ -108,6 +109,19 @@ rv_status rv_result_export(rv_result* r, int64_t batch, struct ArrowArray* out_a
 rv_status rv_result_export_device(rv_result* r, int64_t batch, struct ArrowDeviceArray* out_array, struct ArrowSchema* out_schema);
 
 void rv_result_free(rv_result* r);
+
+/* ---- encode (Arrow -> Avro) ----------------------------------------------------------------------------
+ * Replaces ruhvro::serialize::serialize_record_batch (ruhvro/src/serialize.rs:38-67) + fast_encode::serialize_chunk
+ * (ruhvro/src/fast_encode.rs:27-53) on the GPU.  `batch` / `batch_schema` are the RecordBatch as an Arrow C Data
+ * struct array + schema (host buffers; slices/offsets allowed); OWNERSHIP MOVES to the callee, which releases
+ * both.  Arrow columns are matched to Avro fields by NAME (fast_encode.rs:157-181); a missing column, a type the
+ * reference's downcast would reject, an enum text outside the symbols or a union type id out of range are errors.
+ * Rows are sliced into num_chunks chunks like slice_struct (:19-30); chunk i is exported as a Binary array
+ * (i32 offsets + datum bytes), the GenericBinaryArray<i32> of the reference. */
+rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct ArrowSchema* batch_schema, int64_t num_chunks, rv_encoded** out);
+int64_t rv_encoded_num_chunks(const rv_encoded* r);
+rv_status rv_encoded_export(rv_encoded* r, int64_t chunk, struct ArrowArray* out_array, struct ArrowSchema* out_schema);
+void rv_encoded_free(rv_encoded* r);
 
 /* ---- multi-GPU: fix-ups for gathering shard-local batches into ONE RecordBatch -------------------------
  * Records shard by message; each rank decodes its contiguous range (exactly the reference's per-chunk batches,

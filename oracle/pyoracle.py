@@ -1039,3 +1039,162 @@ def random_schema_json(rng, max_depth: int = 3) -> str:
 
     top = {"type": "record", "name": "Top", "fields": [{"name": nm("c"), "type": typ(0)} for _ in range(rng.randint(1, 6))]}
     return json.dumps(top)
+
+
+# --------------------------------------------------------------------------- #
+# Arrow -> Avro: pure-Python restatement of ruhvro/src/fast_encode.rs (test oracle for the
+# serialize direction).  Walks pyarrow arrays through their raw buffers so that null slots of
+# NON-nullable Avro fields encode whatever value the slot holds, exactly like `array.value(row)`
+# in the reference (fast_encode.rs:401-409).
+# --------------------------------------------------------------------------- #
+class EncodeError(ValueError):
+    pass
+
+
+def _bit(buf: Optional[pa.Buffer], i: int) -> bool:
+    if buf is None:
+        return True
+    return bool((buf.to_pybytes()[i >> 3] >> (i & 7)) & 1) if False else bool((memoryview(buf)[i >> 3] >> (i & 7)) & 1)
+
+
+class _Enc:
+    def __init__(self, s: AvroSchema, arr: pa.Array, nullable=False, null_first=False):
+        self.s, self.k, self.nullable, self.null_first = s, s.kind, nullable, null_first
+        self.arr = arr
+        self.off = arr.offset if arr is not None else 0
+        bufs = arr.buffers() if arr is not None else []
+        self.validity = bufs[0] if bufs else None
+        self.children: List[_Enc] = []
+        t = arr.type if arr is not None else None
+        k = self.k
+        if k in ("int", "date"):
+            self._need(pa.types.is_int32(t) or pa.types.is_date32(t), "Int32/Date32")
+        elif k in ("long", "timestamp-millis", "timestamp-micros"):
+            self._need(pa.types.is_int64(t) or pa.types.is_timestamp(t), "Int64/Timestamp")
+        elif k == "float":
+            self._need(pa.types.is_float32(t), "Float32")
+        elif k == "double":
+            self._need(pa.types.is_float64(t), "Float64")
+        elif k == "boolean":
+            self._need(pa.types.is_boolean(t), "Boolean")
+        elif k in ("string", "enum"):
+            self._need(pa.types.is_string(t), "Utf8")
+        elif k == "record":
+            self._need(pa.types.is_struct(t), "Struct")
+            names = [t.field(i).name for i in range(t.num_fields)]
+            for fname, fs, _ in s.fields:  # match by NAME (fast_encode.rs:157-181)
+                if fname not in names:
+                    raise EncodeError(f"Arrow struct missing column '{fname}' required by Avro schema. Available columns: {names}")
+                self.children.append(_make_enc(fs, arr.field(names.index(fname)) if arr.offset == 0 else arr.field(names.index(fname))))
+        elif k == "union":
+            self._need(pa.types.is_union(t) and t.mode == "sparse", "sparse Union")
+            for i, v in enumerate(s.variants):
+                self.children.append(_make_enc(v, arr.field(i)))
+        elif k == "array":
+            self._need(pa.types.is_list(t) and not pa.types.is_map(t), "List")
+            self.children.append(_make_enc(s.items, arr.values))
+        elif k == "map":
+            self._need(pa.types.is_map(t), "Map")
+            self.children.append(_Enc(AvroSchema("string"), arr.keys))
+            self.children.append(_make_enc(s.values, arr.items))
+
+    def _need(self, ok, what):
+        if not ok:
+            raise EncodeError(f"fast_encode: arrow array downcast failed (expected {what}, got {self.arr.type})")
+
+
+def _make_enc(s: AvroSchema, arr: pa.Array) -> _Enc:
+    if s.kind == "union" and len(s.variants) == 2 and any(v.kind == "null" for v in s.variants):
+        null_first = s.variants[0].kind == "null"
+        inner = s.variants[1] if null_first else s.variants[0]
+        if inner.kind in ("null", "union"):
+            raise EncodeError("fast_encode: unsupported nullable inner type")
+        return _Enc(inner, arr, True, null_first)
+    if s.kind == "null":
+        e = _Enc.__new__(_Enc)
+        e.s, e.k, e.nullable, e.null_first, e.arr, e.off, e.validity, e.children = s, "null", False, False, arr, 0, None, []
+        return e
+    return _Enc(s, arr)
+
+
+def _np_view(buf: pa.Buffer, dtype):
+    import numpy as np
+    return np.frombuffer(buf, dtype=dtype)
+
+
+def _write(e: _Enc, row: int, out: bytearray):
+    """FieldEncoder::write (fast_encode.rs:397-502); `row` is the logical row of e.arr."""
+    k = e.k
+    if k == "null":
+        return
+    i = row + e.off
+    if e.nullable:
+        is_null = e.validity is not None and not _bit(e.validity, i)
+        out += zigzag_bytes((0 if e.null_first else 1) if is_null else (1 if e.null_first else 0))
+        if is_null:
+            return
+    bufs = e.arr.buffers()
+    if k in ("int", "date"):
+        out += zigzag_bytes(int(_np_view(bufs[1], "<i4")[i]))
+    elif k in ("long", "timestamp-millis", "timestamp-micros"):
+        out += zigzag_bytes(int(_np_view(bufs[1], "<i8")[i]))
+    elif k == "float":
+        out += bytes(memoryview(bufs[1])[4 * i:4 * i + 4])
+    elif k == "double":
+        out += bytes(memoryview(bufs[1])[8 * i:8 * i + 8])
+    elif k == "boolean":
+        out.append(1 if _bit(bufs[1], i) else 0)
+    elif k in ("string", "enum"):
+        offs = _np_view(bufs[1], "<i4")
+        s0, s1 = int(offs[i]), int(offs[i + 1])
+        raw = bytes(memoryview(bufs[2])[s0:s1]) if bufs[2] is not None else b""
+        if k == "string":
+            out += zigzag_bytes(len(raw))
+            out += raw
+        else:
+            sym = raw.decode("utf-8", "replace")
+            if sym not in e.s.symbols:
+                raise EncodeError(f"fast_encode: enum symbol '{sym}' not in schema")
+            out += zigzag_bytes(e.s.symbols.index(sym))
+    elif k == "record":
+        for ch in e.children:  # children of a struct share the struct's logical row (+ the struct's offset)
+            _write(ch, i, out)
+    elif k == "union":
+        tid = int(_np_view(bufs[0] if len(bufs) == 1 else bufs[1], "i1")[i])
+        if tid < 0 or tid >= len(e.children):
+            raise EncodeError(f"fast_encode: union type_id {tid} out of range")
+        out += zigzag_bytes(tid)
+        _write(e.children[tid], i, out)
+    else:  # array / map (ListEncoder / MapEncoder :518-554)
+        offs = _np_view(bufs[1], "<i4")
+        s0, s1 = int(offs[i]), int(offs[i + 1])
+        if s1 > s0:
+            out += zigzag_bytes(s1 - s0)
+            for j in range(s0, s1):
+                if k == "map":
+                    _write(e.children[0], j, out)
+                    _write(e.children[1], j, out)
+                else:
+                    _write(e.children[0], j, out)
+        out += zigzag_bytes(0)
+
+
+def py_encode(schema: AvroSchema, batch: pa.RecordBatch, num_chunks: int = 1) -> List[List[bytes]]:
+    """serialize_record_batch (serialize.rs:38-67) + serialize_chunk (fast_encode.rs:27-53): one list of
+    datums per chunk."""
+    if not is_supported(schema):
+        raise EncodeError("schema not supported by the direct encoder")
+    sa = batch.to_struct_array()
+    top = _Enc(schema, sa)
+    n = batch.num_rows
+    k = clamp_chunks(num_chunks, n)
+    out = []
+    for r0, r1 in chunk_bounds(n, k):
+        rows = []
+        for r in range(r0, r1):
+            b = bytearray()
+            for ch in top.children:
+                _write(ch, r + top.off, b)
+            rows.append(bytes(b))
+        out.append(rows)
+    return out

@@ -78,6 +78,12 @@ def _load():
     L.rv_result_export_device.argtypes = [vp, i64, vp, vp]
     L.rv_result_free.argtypes = [vp]
     L.rv_result_free.restype = None
+    L.rv_encode_host.argtypes = [vp, vp, vp, i64, ctypes.POINTER(vp)]
+    L.rv_encoded_num_chunks.restype = i64
+    L.rv_encoded_num_chunks.argtypes = [vp]
+    L.rv_encoded_export.argtypes = [vp, i64, vp, vp]
+    L.rv_encoded_free.argtypes = [vp]
+    L.rv_encoded_free.restype = None
     L.rv_host_alloc.restype = vp
     L.rv_host_alloc.argtypes = [ctypes.c_size_t]
     L.rv_host_free.argtypes = [vp]
@@ -235,10 +241,28 @@ def decode_packed(data, offsets, n: int, schema: str, num_chunks: int = 1) -> Li
 
 
 def serialize_record_batch(data, schema, num_chunks):
-    """Arrow -> Avro (src/lib.rs:91-106).  The GPU encode path is SURVEY.md 8(f) rank 1 ("next");
-    it is not built yet and, by design, there is no CPU stand-in."""
-    raise NotImplementedError("serialize_record_batch: the GPU Arrow->Avro encoder is not built yet (SURVEY.md 8(f))")
+    """pyarrow.RecordBatch -> `num_chunks` pyarrow Binary arrays of schemaless Avro datums
+    (src/lib.rs:91-106; ruhvro/src/serialize.rs:38-67), encoded on the GPU (rv_encode_host)."""
+    if not isinstance(data, pa.RecordBatch):
+        raise TypeError("argument 'data': expected a pyarrow.RecordBatch")
+    if num_chunks < 0:
+        raise OverflowError("can't convert negative int to unsigned")
+    s = _get_or_parse_schema(schema)
+    c_arr, c_sch = _ArrowArray(), _ArrowSchema()
+    data._export_to_c(ctypes.addressof(c_arr), ctypes.addressof(c_sch))
+    h = ctypes.c_void_p()
+    _check(lib.rv_encode_host(s.handle, ctypes.addressof(c_arr), ctypes.addressof(c_sch), int(num_chunks), ctypes.byref(h)))
+    try:
+        out = []
+        for i in range(lib.rv_encoded_num_chunks(h)):
+            a, sc = _ArrowArray(), _ArrowSchema()
+            _check(lib.rv_encoded_export(h, i, ctypes.addressof(a), ctypes.addressof(sc)))
+            out.append(pa.Array._import_from_c(ctypes.addressof(a), ctypes.addressof(sc)))
+        return out
+    finally:
+        lib.rv_encoded_free(h)
 
 
 def serialize_record_batch_spawn(data, schema, num_chunks):
+    """Same results as serialize_record_batch (the reference only changes the tokio primitive, serialize.rs:70-99)."""
     return serialize_record_batch(data, schema, num_chunks)

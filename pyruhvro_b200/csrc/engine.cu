@@ -998,6 +998,10 @@ rv_status rv_dev_concat_bits(uint32_t* d_dst_words, int64_t dst_bit, const uint3
     return RV_OK;
 }
 
+// used by encode.cu (same library, separate translation unit)
+const void* rv_schema_avro_root(const rv_schema* s) { return s ? s->avro.get() : nullptr; }
+void rv_set_last_error(const char* msg) { t_error = msg ? msg : ""; }
+
 const char* rv_last_walker(void) { return t_walker; }
 long long rv_last_overflow_tiles(void) { return t_overflow_tiles; }
 void rv_set_jit_enabled(int enabled) { g_jit_override.store(enabled < 0 ? -1 : (enabled ? 1 : 0)); }
