@@ -135,5 +135,16 @@ def test_decode_without_gpu_fails_loudly():
         import numpy as np
         data, off = po.pack_records([bytes.fromhex(G.G2_HEX)])
         pr.decode_packed(data, off, 1, G.G2_SCHEMA, 1)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError) as e:   # encode has no CPU path either
+        pr.serialize_record_batch(pa.record_batch({"firstName": ["a"], "lastName": ["b"], "age": pa.array([1], pa.int32()),
+                                                   "addresses": pa.array([[]], pa.list_(pa.struct([("street", pa.string()), ("city", pa.string()), ("zipCode", pa.string())]))),
+                                                   "email": ["x"]}), G.G2_SCHEMA, 1)
+    assert "CUDA" in str(e.value)
+
+
+def test_encode_plan_errors_need_no_gpu():
+    with pytest.raises(ValueError) as e:
+        pr.serialize_record_batch(pa.record_batch({"x": [1]}), G.G2_SCHEMA, 1)
+    assert "Arrow struct missing column 'firstName' required by Avro schema. Available columns: [\"x\"]" in str(e.value)
+    with pytest.raises(TypeError):
         pr.serialize_record_batch(None, G.G2_SCHEMA, 1)
