@@ -27,7 +27,7 @@ def test_random_schemas(coracle, seed):
     assert_matches_oracle(coracle, emu.decode(sj, data, off, len(recs), k), sj, data, off, len(recs), k)
 
 
-@pytest.mark.parametrize("seed", range(100, 124))
+@pytest.mark.parametrize("seed", range(100, 112))
 def test_generated_walker_random_schemas(coracle, seed):
     """The schema-specialised walker source that NVRTC compiles for the GPU, compiled for the host."""
     sj, recs, data, off = gen_case(seed)
