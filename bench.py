@@ -308,6 +308,24 @@ def main():
 
     cpu = cpu_arm(args, args.workload, steps=3, warmup=1, emit_line=False) if world == 1 else None
 
+    # ---- the reverse direction, informational: Arrow -> Avro through serialize_record_batch ----
+    encode = None
+    if world == 1:
+        try:
+            batch = pr.decode_packed(h_data, h_off, n, schema_json, 1)[0]
+            for _ in range(2):
+                pr.serialize_record_batch(batch, schema_json, args.num_chunks)
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                out = pr.serialize_record_batch(batch, schema_json, args.num_chunks)
+            dt = (time.perf_counter() - t0) / reps
+            encode = {"value": n / dt, "unit": UNIT, "ms_per_step": 1000.0 * dt, "path": "pyruhvro.serialize_record_batch (host Arrow in, host Avro out)",
+                      "avro_bytes": int(sum(a.nbytes for a in out))}
+            del out, batch
+        except Exception as e:  # pragma: no cover
+            encode = {"error": str(e)[:200]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -329,6 +347,8 @@ def main():
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if encode is not None:
+        line["encode"] = encode
     print(json.dumps(line), flush=True)
     for p in pinned_blocks:
         L.rv_host_free(p)

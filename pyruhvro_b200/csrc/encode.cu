@@ -59,6 +59,7 @@ struct EncParams {
     unsigned long long* err;
     uint8_t* const* out_data;   // [k]
     int32_t* const* out_offsets;  // [k]
+    uint32_t stage_cap;   // bytes of dynamic shared memory in which a tile's datums are assembled
 };
 
 namespace {
@@ -232,6 +233,14 @@ __global__ void __launch_bounds__(kBlock) encode_write_kernel(const EncParams p)
     uint32_t base = p.tile_base[blockIdx.x];
     for (int w = 0; w < warp; ++w) base += s_w[w];
     const uint32_t off = base + incl - sz;
+    // The tile's datums are contiguous in the output ([tile_base, tile_base + tile_total)): assemble them in
+    // shared memory (per-lane byte stores are cheap there) and write the tile out with coalesced 128-bit stores.
+    extern __shared__ __align__(16) uint8_t enc_smem[];
+    const uint32_t tile_base = p.tile_base[blockIdx.x];
+    const uint32_t tile_total = p.tile_agg[blockIdx.x];
+    uint8_t* gout = p.out_data[chunk] + tile_base;
+    const uint32_t galign = uint32_t(reinterpret_cast<uintptr_t>(gout) & 15u);
+    const bool staged = tile_total + galign <= p.stage_cap;
     if (tid < nrec) {
         int32_t* offs = p.out_offsets[chunk];
         const int64_t i = int64_t(local) * kBlock + tid;  // row inside the chunk
@@ -239,9 +248,27 @@ __global__ void __launch_bounds__(kBlock) encode_write_kernel(const EncParams p)
         offs[i + 1] = int32_t(off + sz);
         EncCtx c;
         enc_init(c, p);
-        c.out = p.out_data[chunk] + off;
+        c.out = staged ? enc_smem + galign + (off - tile_base) : p.out_data[chunk] + off;
         enc_range<1, 0>(c, 0, p.n_nodes, r0 + tid);
     }
+    if (staged) {
+        __syncthreads();
+        const uint32_t head = min(tile_total, (16u - galign) & 15u);
+        for (uint32_t i = tid; i < head; i += kBlock) gout[i] = enc_smem[galign + i];
+        const uint32_t nvec = (tile_total - head) >> 4;
+        const uint4* sv = reinterpret_cast<const uint4*>(enc_smem + galign + head);
+        uint4* gv = reinterpret_cast<uint4*>(gout + head);
+        for (uint32_t i = tid; i < nvec; i += kBlock) gv[i] = sv[i];
+        for (uint32_t i = head + (nvec << 4) + tid; i < tile_total; i += kBlock) gout[i] = enc_smem[galign + i];
+    }
+}
+
+// max over tiles of the tile's output bytes (sizes the staging area)
+__global__ void encode_tile_max_kernel(const EncParams p, unsigned long long* out_max) {
+    unsigned long long m = 0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < p.n_tiles; t += gridDim.x * blockDim.x) m = max(m, (unsigned long long)p.tile_agg[t]);
+    for (int d = 16; d; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, m, d); if (o > m) m = o; }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out_max, m);
 }
 
 // per-chunk exclusive scan of the tile totals (one CTA per chunk)
@@ -433,10 +460,23 @@ struct EncBuilder {
     }
 };
 
-struct DevMem {
+}  // namespace
+}  // namespace rv
+extern "C" void* rv_internal_dev_get(size_t bytes, int device, size_t* actual);
+extern "C" void rv_internal_dev_put(void* p, size_t actual, int device);
+namespace rv {
+namespace {
+
+struct DevMem {  // from the library's device-memory cache (blocks return after the stream was synchronised)
     void* p = nullptr;
-    ~DevMem() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+    size_t actual = 0;
+    int device = 0;
+    ~DevMem() { if (p) rv_internal_dev_put(p, actual, device); }
+    cudaError_t alloc(size_t n) {
+        if (cudaGetDevice(&device) != cudaSuccess) return cudaErrorInvalidDevice;
+        p = rv_internal_dev_get(n ? n : 1, device, &actual);
+        return p ? cudaSuccess : cudaErrorMemoryAllocation;
+    }
 };
 
 }  // namespace
@@ -535,11 +575,12 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
     const int64_t n_tiles = n > 0 ? tpc * (k - 1) + (last_rows + kBlock - 1) / kBlock : 0;
     p.tiles_per_chunk = int32_t(tpc); p.n_tiles = int32_t(n_tiles);
     std::vector<unsigned long long> chunk_tot(static_cast<size_t>(k), 0ull);
+    unsigned long long max_tile = 0;
     if (n > 0) {
         ENC_CUDA(d_rowsize.alloc(size_t(n) * 4));
         ENC_CUDA(d_agg.alloc(size_t(n_tiles) * 4));
         ENC_CUDA(d_base.alloc(size_t(n_tiles) * 4));
-        ENC_CUDA(d_err.alloc(8));
+        ENC_CUDA(d_err.alloc(16));
         ENC_CUDA(d_tot.alloc(size_t(k) * 8));
         ENC_CUDA(cudaMemsetAsync(d_err.p, 0xFF, 8, nullptr));
         p.row_size = static_cast<uint32_t*>(d_rowsize.p); p.tile_agg = static_cast<uint32_t*>(d_agg.p);
@@ -548,8 +589,11 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
         int thr = 32;
         while (thr < 1024 && thr < tpc) thr <<= 1;
         encode_scan_kernel<<<unsigned(k), thr>>>(p, static_cast<unsigned long long*>(d_tot.p));
+        ENC_CUDA(cudaMemsetAsync(static_cast<uint8_t*>(d_err.p) + 8, 0, 8, nullptr));
+        encode_tile_max_kernel<<<std::max(1, std::min(int((n_tiles + 255) / 256), 592)), 256>>>(p, static_cast<unsigned long long*>(d_err.p) + 1);
         ENC_CUDA(cudaGetLastError());
         unsigned long long err_word = ~0ull;
+        ENC_CUDA(cudaMemcpyAsync(&max_tile, static_cast<uint8_t*>(d_err.p) + 8, 8, cudaMemcpyDeviceToHost, nullptr));
         ENC_CUDA(cudaMemcpyAsync(&err_word, d_err.p, 8, cudaMemcpyDeviceToHost, nullptr));
         ENC_CUDA(cudaMemcpyAsync(chunk_tot.data(), d_tot.p, size_t(k) * 8, cudaMemcpyDeviceToHost, nullptr));
         ENC_CUDA(cudaStreamSynchronize(nullptr));
@@ -582,7 +626,17 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
         ENC_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(d_ptrs.p) + size_t(k) * 8, h_offs.data(), size_t(k) * 8, cudaMemcpyHostToDevice, nullptr));
         p.out_data = static_cast<uint8_t* const*>(d_ptrs.p);
         p.out_offsets = reinterpret_cast<int32_t* const*>(static_cast<uint8_t*>(d_ptrs.p) + size_t(k) * 8);
-        encode_write_kernel<<<unsigned(n_tiles), kBlock>>>(p);
+        // staging area: the largest tile (+ alignment), capped so at least two CTAs share an SM
+        size_t stage = std::min<size_t>(size_t(max_tile) + 32, 100 * 1024);
+        stage = (stage + 63) & ~size_t(63);
+        static bool attr_set = false;
+        if (!attr_set) {
+            ENC_CUDA(cudaFuncSetAttribute(encode_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+            ENC_CUDA(cudaFuncSetAttribute(encode_write_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            attr_set = true;
+        }
+        p.stage_cap = uint32_t(stage);
+        encode_write_kernel<<<unsigned(n_tiles), kBlock, stage>>>(p);
         ENC_CUDA(cudaGetLastError());
     }
     for (int j = 0; j < k; ++j) {

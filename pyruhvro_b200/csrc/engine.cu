@@ -999,6 +999,8 @@ rv_status rv_dev_concat_bits(uint32_t* d_dst_words, int64_t dst_bit, const uint3
 }
 
 // used by encode.cu (same library, separate translation unit)
+void* rv_internal_dev_get(size_t bytes, int device, size_t* actual) { return devmem().get(bytes, device, actual); }
+void rv_internal_dev_put(void* p, size_t actual, int device) { devmem().put(p, actual, device); }
 const void* rv_schema_avro_root(const rv_schema* s) { return s ? s->avro.get() : nullptr; }
 void rv_set_last_error(const char* msg) { t_error = msg ? msg : ""; }
 
