@@ -138,6 +138,32 @@ def test_pipelined_chunks_large_batch(coracle, walker):
     assert "(record 20000)" in str(e.value) and "varint" in str(e.value)   # first failing chunk wins
 
 
+def test_concurrent_calls_from_python_threads(coracle):
+    """The reference releases the GIL and is re-entrant (src/lib.rs:82-87); so is this library."""
+    import threading
+    import workloads
+    cases = []
+    for i, name in enumerate(("kafka", "flat", "wide", "array_map")):
+        sj, data, off = workloads.generate(name, 20_000 + 1000 * i, seed=20 + i)
+        cases.append((sj, data, off, 20_000 + 1000 * i))
+    errors = []
+
+    def work(case, reps):
+        sj, data, off, n = case
+        try:
+            for r in range(reps):
+                assert_matches_oracle(coracle, pr.decode_packed(data, off, n, sj, 1 + r % 3), sj, data, off, n, 1 + r % 3, full_validate=False)
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(c, 4)) for c in cases for _ in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:2]
+
+
 def test_error_surface():
     with pytest.raises(TypeError):
         pr.deserialize_array([b"ok", "not-bytes"], G.G1_SCHEMA)
