@@ -842,7 +842,9 @@ rv_status rv_decode_host(const rv_schema* s_, const uint8_t* data, const int64_t
     if (st) return st;
     const int64_t k = clamp_chunks(num_chunks, n);
     float h2d = 0, d2h = 0;
-    if (k < 2 || n < 65536 || !pipeline_enabled()) {
+    // pipelining pays when every chunk is big enough to amortise its own launches and copies; many small
+    // chunks go through ONE launch set that handles all chunks at once
+    if (k < 2 || n / k < 16384 || !pipeline_enabled()) {
         st = decode_host_range(s, data, offsets, 0, n, num_chunks, nullptr, device, out, &h2d, &d2h);
         t_timings[4] = h2d;
         t_timings[5] = d2h;

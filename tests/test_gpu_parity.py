@@ -75,6 +75,15 @@ def test_random_schemas_interp(coracle, seed):
 def test_packed_c_abi_path(coracle, walker):
     sj, recs, data, off = gen_case(7, n=5000)
     assert_matches_oracle(coracle, pr.decode_packed(data, off, len(recs), sj, 8), sj, data, off, len(recs), 8)
+    # a window into a larger packed buffer: offsets[0] != 0 (absolute offsets are kept, the base is biased)
+    sub_off = off[777:]
+    got = pr.decode_packed(data, sub_off, len(recs) - 777, sj, 3)
+    data2, off2 = po.pack_records(recs[777:])
+    assert_matches_oracle(coracle, got, sj, data2, off2, len(recs) - 777, 3)
+    # more chunks than the pipeline wants to run separately: one launch set handles all of them
+    import workloads
+    sjk, dk, ok = workloads.generate("kafka", 70_000, seed=4)
+    assert_matches_oracle(coracle, pr.decode_packed(dk, ok, 70_000, sjk, 64), sjk, dk, ok, 70_000, 64, full_validate=False)
 
 
 def test_empty_and_partition(coracle):
