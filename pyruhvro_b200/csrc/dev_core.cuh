@@ -279,7 +279,16 @@ RV_HD void copy_from_record(C& c, int slot_b, int stream, uint32_t o, uint32_t s
                 atomicOr(dw, v & m_first & m_last);
             } else {
                 atomicOr(dw, v & m_first);
-                for (uint32_t j = 1; j + 1 < nwords; ++j) {
+                uint32_t j = 1;
+                for (; j + 4 < nwords; j += 4) {  // four interior words per trip: the loop overhead dominates otherwise
+                    const uint32_t w1 = sw[j + 1], w2 = sw[j + 2], w3 = sw[j + 3], w4 = sw[j + 4];
+                    dw[j] = __funnelshift_r(hi, w1, sh);
+                    dw[j + 1] = __funnelshift_r(w1, w2, sh);
+                    dw[j + 2] = __funnelshift_r(w2, w3, sh);
+                    dw[j + 3] = __funnelshift_r(w3, w4, sh);
+                    hi = w4;
+                }
+                for (; j + 1 < nwords; ++j) {
                     lo = hi;
                     hi = sw[j + 1];
                     dw[j] = __funnelshift_r(lo, hi, sh);

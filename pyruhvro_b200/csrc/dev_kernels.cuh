@@ -28,8 +28,10 @@ struct Tile {
 __device__ __forceinline__ Tile tile_of(const DecodeParams& p, int tile) {
     Tile t;
     int j = 0;
-    if (p.k > 1) {
-        j = tile / p.tiles_per_chunk;
+    if (p.k > 1) {  // tile / tiles_per_chunk without the ~40-instruction integer division: estimate and correct
+        j = int(__fdividef(float(tile), float(p.tiles_per_chunk)));
+        while (j > 0 && j * p.tiles_per_chunk > tile) --j;
+        while ((j + 1) * p.tiles_per_chunk <= tile) ++j;
         if (j > p.k - 1) j = p.k - 1;
     }
     t.chunk = j;
@@ -252,31 +254,37 @@ __device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t,
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // (each record's first row / first byte per stream was loaded into `cur` by stage_in: the chunk-relative
     // tile base from scan_kernel + the record's prefix inside the tile from the count kernel)
-    if (tid < p.n_streams) {
-        const uint32_t tb = __ldg(p.tile_base + size_t(tid) * p.n_tiles + tile_id);
-        tbase[tid] = tb;
-        tot[tid] = __ldg(p.tile_agg + size_t(tid) * p.n_tiles + tile_id);
-        const int slot = p.stream_slot[tid];
-        tbase[p.n_streams + tid] = slot >= 0 ? uint32_t(reinterpret_cast<uintptr_t>(static_cast<uint8_t*>(buf_ptr(c, slot)) + tb) & 15u) : 0u;
-    }
-    __syncthreads();
-    // Staging map of the Utf8 streams.  Stream s's bytes of this tile occupy [tile_base, tile_base + tot)
-    // of its Arrow data buffer; in shared memory its region starts at an offset congruent (mod 16) to the
-    // global destination so the write-out can use aligned uint4.
-    if (tid == 0) {
-        uint32_t off = 0;
-        bool fits = p.smem_stage_cap > 0;
-        for (int s = 0; s < p.n_streams; ++s) {
-            if (p.stream_slot[s] >= 0) {
-                const uint32_t start = ((off + 15u) & ~15u) + tbase[p.n_streams + s];
-                adj[s] = start - tbase[s];  // staging offset of chunk-relative byte `o` = adj + o
-                off = start + tot[s];
-                if (off > p.smem_stage_cap) fits = false;
-            } else {
-                adj[s] = 0;
+    // Staging map of the Utf8 streams, computed by warp 0 with a shuffle scan.  Stream s's bytes of this tile
+    // occupy [tile_base, tile_base + tot) of its Arrow data buffer; in shared memory its region starts at a
+    // 16-byte boundary plus the destination's misalignment, so the write-out can use aligned uint4.
+    if (warp == 0) {
+        uint32_t carry = 0;
+        for (int s0 = 0; s0 < p.n_streams; s0 += 32) {
+            const int s = s0 + lane;
+            uint32_t tb = 0, tt = 0, ga = 0, region = 0;
+            int slot = -1;
+            if (s < p.n_streams) {
+                tb = __ldg(p.tile_base + size_t(s) * p.n_tiles + tile_id);
+                tt = __ldg(p.tile_agg + size_t(s) * p.n_tiles + tile_id);
+                slot = p.stream_slot[s];
+                if (slot >= 0) {
+                    ga = uint32_t(reinterpret_cast<uintptr_t>(static_cast<uint8_t*>(buf_ptr(c, slot)) + tb) & 15u);
+                    region = (tt + ga + 15u) & ~15u;
+                }
             }
+            uint32_t incl = region;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += u;
+            }
+            if (s < p.n_streams) {
+                tbase[s] = tb;
+                tot[s] = tt;
+                adj[s] = slot >= 0 ? (carry + incl - region + ga) - tb : 0u;  // staging offset of chunk-relative byte o = adj + o
+            }
+            carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
-        tot[p.n_streams] = fits ? 1u : 0u;
+        if (lane == 0) tot[p.n_streams] = (p.smem_stage_cap > 0 && carry <= p.smem_stage_cap) ? 1u : 0u;
     }
     __syncthreads();
     const bool stage_on = p.n_streams > 0 && tot[p.n_streams] != 0;
