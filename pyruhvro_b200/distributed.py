@@ -215,12 +215,66 @@ def gather_batch(local: List[dict], schema: pa.Schema, group=None, ops=None, dev
             f["bufs"].append(dst)
         final.append(f)
     if device != "cpu":
-        torch.cuda.current_stream().synchronize()
+        _stage_to_pinned(final)
     return _to_arrow(final, schema)
 
 
+class _PinnedBlock:
+    """One pinned host slab (library cache) that backs every buffer of a gathered batch; freed when the last
+    pyarrow buffer referencing it dies."""
+
+    def __init__(self, nbytes: int):
+        from . import lib
+        self._lib = lib
+        self.ptr = lib.rv_host_alloc(max(nbytes, 64))
+        if not self.ptr:
+            raise MemoryError("rv_host_alloc failed")
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            self._lib.rv_host_free(self.ptr)
+            self.ptr = None
+
+
+def _stage_to_pinned(flat: List[dict]) -> None:
+    """Device tensors -> one pinned slab with async copies on the current stream and a single sync; the
+    entries of `flat` are replaced by zero-copy pyarrow buffers over the slab."""
+    import torch
+    tensors = []
+    for d in flat:
+        if d["validity"] is not None:
+            tensors.append((d, "validity", None))
+        for i in range(len(d["bufs"])):
+            tensors.append((d, "bufs", i))
+    sizes = [((d[k] if i is None else d[k][i]).numel() + 63) // 64 * 64 for d, k, i in tensors]
+    block = _PinnedBlock(sum(sizes))
+    cudart = torch.cuda.cudart()
+    stream = torch.cuda.current_stream().cuda_stream
+    off = 0
+    for (d, k, i), sz in zip(tensors, sizes):
+        t = d[k] if i is None else d[k][i]
+        n = t.numel()
+        if n:
+            err = cudart.cudaMemcpyAsync(block.ptr + off, t.data_ptr(), n, 2, stream)  # 2 = cudaMemcpyDeviceToHost
+            if int(err[0] if isinstance(err, tuple) else err) != 0:
+                raise RuntimeError(f"cudaMemcpyAsync failed: {err}")
+        buf = pa.foreign_buffer(block.ptr + off, n, base=block)
+        if i is None:
+            d[k] = buf
+        else:
+            d[k][i] = buf
+        off += sz
+    torch.cuda.current_stream().synchronize()
+
+
 def _np(t) -> pa.Buffer:
+    if isinstance(t, pa.Buffer):
+        return t
     return pa.py_buffer(t.cpu().numpy().tobytes()) if t.numel() else pa.py_buffer(b"")
+
+
+def _head(t, nbytes: int):
+    return t.slice(0, nbytes) if isinstance(t, pa.Buffer) else t[:nbytes]
 
 
 def _to_arrow(flat: List[dict], schema: pa.Schema) -> pa.RecordBatch:
@@ -231,7 +285,7 @@ def _to_arrow(flat: List[dict], schema: pa.Schema) -> pa.RecordBatch:
         d = flat[pos]
         pos += 1
         n, nc = d["rows"], d["null_count"]
-        v = _np(d["validity"][: (n + 7) // 8]) if d["validity"] is not None else None
+        v = _np(_head(d["validity"], (n + 7) // 8)) if d["validity"] is not None else None
         kids = [rec(ct) for ct in _children_types(t)]
         if pa.types.is_null(t):
             return pa.nulls(n)
@@ -240,7 +294,7 @@ def _to_arrow(flat: List[dict], schema: pa.Schema) -> pa.RecordBatch:
         if pa.types.is_struct(t):
             return pa.Array.from_buffers(t, n, [v], null_count=nc, children=kids)
         if pa.types.is_boolean(t):
-            return pa.Array.from_buffers(t, n, [v, _np(d["bufs"][0][: (n + 7) // 8])], null_count=nc)
+            return pa.Array.from_buffers(t, n, [v, _np(_head(d["bufs"][0], (n + 7) // 8))], null_count=nc)
         if pa.types.is_string(t):
             return pa.Array.from_buffers(t, n, [v, _np(d["bufs"][0]), _np(d["bufs"][1])], null_count=nc)
         if pa.types.is_list(t) or pa.types.is_map(t):
