@@ -149,6 +149,9 @@ int rv_last_launch_count(void);
  * with NVRTC for the device's architecture) or "interp" (the statically compiled generic kernels).
  * Both are GPU paths; RV_JIT=0 in the environment forces "interp". */
 const char* rv_last_walker(void);
+/* Why the schema-specialised kernels are / are not in use for this schema ("ok", the NVRTC log, ...).
+ * The returned string is valid until the calling thread's next library call. */
+const char* rv_schema_jit_status(const rv_schema* s);
 /* Tiles of the last decode on this thread that did not fit the shared-memory window of the specialised
  * kernels and were handled by the interpreter overflow pass (diagnostics). */
 long long rv_last_overflow_tiles(void);

@@ -147,9 +147,15 @@ class DeviceCache {
     }
     void put(void* p, size_t actual, int device) {
         if (!p) return;
-        std::lock_guard<std::mutex> g(mu_);
-        free_[device].emplace(actual, p);
-        cached_ += actual;
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            if (cached_ + actual <= kMaxCached) {
+                free_[device].emplace(actual, p);
+                cached_ += actual;
+                return;
+            }
+        }
+        cudaFree(p);  // the cache is full: give the block back to the driver
     }
     void trim(int device) {
         std::lock_guard<std::mutex> g(mu_);
@@ -159,6 +165,7 @@ class DeviceCache {
     }
 
   private:
+    static constexpr size_t kMaxCached = size_t(96) << 30;  // of the B200's 180 GB
     static size_t round(size_t b) {
         const size_t g = b >= (size_t(32) << 20) ? (size_t(4) << 20) : (b >= (size_t(1) << 20) ? (size_t(256) << 10) : 4096);
         return ((b ? b : 1) + g - 1) / g * g;
@@ -699,7 +706,9 @@ void rv_schema_release(rv_schema* s) {
             cudaFree(kv.second.nodes);
             cudaFree(kv.second.sym_off);
             cudaFree(kv.second.sym_bytes);
+            cudaFree(kv.second.stream_slot);
         }
+        if (s->jit.lib) cudaLibraryUnload(s->jit.lib);
         delete s;
     }
 }
@@ -1007,6 +1016,12 @@ const void* rv_schema_avro_root(const rv_schema* s) { return s ? s->avro.get() :
 void rv_set_last_error(const char* msg) { t_error = msg ? msg : ""; }
 
 const char* rv_last_walker(void) { return t_walker; }
+const char* rv_schema_jit_status(const rv_schema* s) {
+    if (!s) return "null schema";
+    std::lock_guard<std::mutex> g(const_cast<rv_schema*>(s)->mu);
+    t_error = s->jit.tried ? s->jit.status : "not attempted yet";
+    return t_error.c_str();
+}
 long long rv_last_overflow_tiles(void) { return t_overflow_tiles; }
 void rv_set_jit_enabled(int enabled) { g_jit_override.store(enabled < 0 ? -1 : (enabled ? 1 : 0)); }
 
