@@ -29,7 +29,7 @@ using EmuWalker = rv::InterpWalker;
 using namespace rv;
 
 namespace {
-constexpr int kTile = 256;
+constexpr int kTile = rv::kBlock;
 
 struct Tile { int chunk; int64_t r0; int nrec; int local; };
 
