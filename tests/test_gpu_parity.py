@@ -3,6 +3,8 @@ against the C oracle on the same bytes, buffer-for-buffer.  Needs a B200: `pytes
 import random
 
 import numpy as np
+import pyarrow as pa
+import pyarrow.compute  # noqa: F401
 import pytest
 
 import pyruhvro_b200 as pr
@@ -145,6 +147,39 @@ def test_pipelined_chunks_large_batch(coracle, walker):
     with pytest.raises(ValueError) as e:
         pr.deserialize_array_threaded(recs, M.FLAT, 8)
     assert "(record 20000)" in str(e.value) and "varint" in str(e.value)   # first failing chunk wins
+
+
+def test_i32_offset_ceiling_and_huge_records(coracle):
+    """A Utf8 column of one batch may not exceed 2^31-1 bytes (Arrow i32 offsets; arrow-rs panics, we return
+    RV_ERR_OVERFLOW); split over two chunks the same input decodes.  36 KB records also force every tile through
+    the non-staged (global-memory) interpreter pass."""
+    sj = '{"type":"record","name":"Big","fields":[{"name":"id","type":"long"},{"name":"s","type":"string"}]}'
+    n, slen = 60_000, 36_000
+    body = np.frombuffer((b"0123456789abcdef" * (slen // 16 + 1))[:slen], dtype=np.uint8)
+    head = po.zigzag_bytes(slen)
+    rec_len = 3 + len(head) + slen          # ids below are 3-byte varints
+    data = np.empty(n * rec_len, dtype=np.uint8)
+    view = data.reshape(n, rec_len)
+    ids = np.arange(n, dtype=np.int64) + 70_000
+    zz = (ids << 1).astype(np.uint64)
+    view[:, 0] = (zz & 0x7F) | 0x80
+    view[:, 1] = ((zz >> 7) & 0x7F) | 0x80
+    view[:, 2] = (zz >> 14) & 0x7F
+    view[:, 3:3 + len(head)] = np.frombuffer(head, dtype=np.uint8)
+    view[:, 3 + len(head):] = body
+    off = np.arange(n + 1, dtype=np.int64) * rec_len
+    assert n * slen > 2**31
+    with pytest.raises(ValueError) as e:
+        pr.decode_packed(data, off, n, sj, 1)
+    assert "overflow" in str(e.value)
+    got = pr.decode_packed(data, off, n, sj, 2)
+    assert [b.num_rows for b in got] == [30_000, 30_000]
+    for j, b in enumerate(got):
+        assert b.column("id").to_pylist()[:3] == [70_000 + 30_000 * j + i for i in range(3)]
+        s_col = b.column("s")
+        assert s_col.buffers()[1].size >= 4 * 30_001 and s_col[29_999].as_py() == body.tobytes().decode()
+        assert pa.compute.utf8_length(s_col).to_pylist()[:2] == [slen, slen]
+    assert pr.lib.rv_last_overflow_tiles() >= 0
 
 
 def test_concurrent_calls_from_python_threads(coracle):
