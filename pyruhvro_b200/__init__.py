@@ -30,7 +30,7 @@ from . import _build
 
 __all__ = [
     "deserialize_array", "deserialize_array_threaded", "deserialize_array_threaded_spawn",
-    "serialize_record_batch", "serialize_record_batch_spawn", "lib", "Schema", "decode_packed",
+    "serialize_record_batch", "serialize_record_batch_spawn", "lib", "Schema", "decode_packed", "deserialize_arrow_array",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -238,6 +238,42 @@ def decode_packed(data, offsets, n: int, schema: str, num_chunks: int = 1) -> Li
     h = ctypes.c_void_p()
     _check(lib.rv_decode_host(s.handle, data.ctypes.data if data.size else None, offsets.ctypes.data, n, num_chunks, ctypes.byref(h)))
     return _export_batches(h.value, s)
+
+
+def _packed_view(arr):
+    """(data uint8[], offsets int64[n+1], n) of a Binary / LargeBinary / String array without copying the
+    payload: the offsets are rebased so that offsets[0] indexes into `data` (sliced arrays are fine)."""
+    import numpy as np
+    if isinstance(arr, pa.ChunkedArray):
+        arr = arr.combine_chunks() if arr.num_chunks != 1 else arr.chunk(0)
+    t = arr.type
+    if pa.types.is_large_binary(t) or pa.types.is_large_string(t):
+        odt = np.int64
+    elif pa.types.is_binary(t) or pa.types.is_string(t):
+        odt = np.int32
+    else:
+        raise TypeError(f"expected a (Large)Binary / (Large)String array of Avro datums, got {t}")
+    if arr.null_count:
+        raise ValueError("the datum array contains nulls")
+    n = len(arr)
+    bufs = arr.buffers()
+    if n == 0 or bufs[1] is None:
+        return np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64), 0
+    off = np.frombuffer(bufs[1], dtype=odt)[arr.offset: arr.offset + n + 1]
+    data = np.frombuffer(bufs[2], dtype=np.uint8) if bufs[2] is not None else np.zeros(0, dtype=np.uint8)
+    return data, off.astype(np.int64, copy=False), n
+
+
+def deserialize_arrow_array(array, schema, num_chunks=1):
+    """An Arrow Binary/LargeBinary array (or ChunkedArray) of schemaless datums -> `num_chunks` RecordBatches.
+
+    The ingest shortcut of SURVEY §8(f) rank 2: what `per_datum_deserialize_threaded` builds internally at
+    ruhvro/src/deserialize.rs:90 (a packed values buffer + offsets) is accepted as-is, so there is no Python
+    list walk and no gather copy; results are identical to deserialize_array_threaded on `array.to_pylist()`."""
+    if num_chunks < 0:
+        raise OverflowError("can't convert negative int to unsigned")
+    data, off, n = _packed_view(array)
+    return decode_packed(data, off, n, schema, int(num_chunks))
 
 
 def serialize_record_batch(data, schema, num_chunks):

@@ -148,3 +148,28 @@ def test_encode_plan_errors_need_no_gpu():
     assert "Arrow struct missing column 'firstName' required by Avro schema. Available columns: [\"x\"]" in str(e.value)
     with pytest.raises(TypeError):
         pr.serialize_record_batch(None, G.G2_SCHEMA, 1)
+
+
+def test_arrow_array_ingest_view_is_zero_copy_and_rebased():
+    """deserialize_arrow_array's host-side adapter (no GPU needed): payload is viewed, offsets widened to i64."""
+    import numpy as np
+    import pyarrow as pa
+    recs = [b"ab", b"", b"cdef", b"g" * 40, b"hi"]
+    for typ in (pa.binary(), pa.large_binary()):
+        arr = pa.array(recs, type=typ)
+        data, off, n = pr._packed_view(arr)
+        assert n == 5 and off.dtype == np.int64 and off.tolist() == [0, 2, 2, 6, 46, 48]
+        assert data.ctypes.data == arr.buffers()[2].address          # no copy of the payload
+        sl = arr.slice(2, 2)
+        data, off, n = pr._packed_view(sl)
+        assert n == 2 and off.tolist() == [2, 6, 46] and bytes(data[off[0]:off[1]]) == b"cdef"
+    ch = pa.chunked_array([pa.array(recs[:2], type=pa.binary()), pa.array(recs[2:], type=pa.binary())])
+    data, off, n = pr._packed_view(ch)
+    assert n == 5 and [bytes(data[off[i]:off[i + 1]]) for i in range(5)] == recs
+    assert pr._packed_view(pa.array([], type=pa.binary()))[2] == 0
+    with pytest.raises(ValueError):
+        pr._packed_view(pa.array([b"a", None], type=pa.binary()))
+    with pytest.raises(TypeError):
+        pr._packed_view(pa.array([1, 2]))
+    with pytest.raises(OverflowError):
+        pr.deserialize_arrow_array(pa.array(recs, type=pa.binary()), "{}", -1)

@@ -149,6 +149,20 @@ def test_pipelined_chunks_large_batch(coracle, walker):
     assert "(record 20000)" in str(e.value) and "varint" in str(e.value)   # first failing chunk wins
 
 
+def test_arrow_array_ingest_matches_list_ingest(coracle):
+    """deserialize_arrow_array (Binary / LargeBinary / sliced / chunked) == deserialize_array_threaded on the list."""
+    sj, recs, _, _ = gen_case(7, 300)
+    want = pr.deserialize_array_threaded(recs, sj, 3)
+    large = pa.array(recs, type=pa.large_binary())
+    for arr in (pa.array(recs, type=pa.binary()), large,
+                pa.chunked_array([pa.array(recs[:100], type=pa.binary()), pa.array(recs[100:], type=pa.binary())])):
+        got = pr.deserialize_arrow_array(arr, sj, 3)
+        assert len(got) == len(want) and all(g.equals(w) for g, w in zip(got, want))
+    data, off = po.pack_records(recs[50:250])
+    assert_matches_oracle(coracle, pr.deserialize_arrow_array(large.slice(50, 200), sj, 2), sj, data, off, 200, 2)
+    assert pr.deserialize_arrow_array(pa.array([], type=pa.binary()), sj, 4)[0].num_rows == 0
+
+
 def test_i32_offset_ceiling_and_huge_records(coracle):
     """A Utf8 column of one batch may not exceed 2^31-1 bytes (Arrow i32 offsets; arrow-rs panics, we return
     RV_ERR_OVERFLOW); split over two chunks the same input decodes.  36 KB records also force every tile through
