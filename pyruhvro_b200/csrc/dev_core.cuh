@@ -249,6 +249,54 @@ RV_HD void op_bool(C& c, bool valid, int slot_a, int slot_v, uint32_t row) {  //
     }
 }
 
+#if defined(__CUDA_ARCH__)
+// shared -> shared copy of `len` (> 0) bytes from rv_smem[src] to rv_smem[d], one destination WORD per
+// iteration (the warp's cost is its longest string, so iterations matter).  Destination word j takes 4 source
+// bytes at an arbitrary alignment: two aligned source words + a funnel shift.  The first and last words are
+// shared with the neighbouring strings (written by other lanes), so they are merged with atomicOr into the
+// zero-initialised staging area; interior words are plain stores.  Source reads may touch up to 3 bytes
+// before / 4 bytes after the string: still inside the CTA's shared memory.
+__device__ __forceinline__ void copy_smem_words(const uint32_t d, const uint32_t src, const uint32_t len) {
+    const uint32_t a = d & 3u;
+    const uint32_t nwords = (a + len + 3u) >> 2;
+    const uint32_t sp = src - a;  // source byte that lands in byte 0 of destination word 0
+    const uint32_t sh = (sp & 3u) * 8u;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(rv_smem + (sp & ~3u));
+    uint32_t* dw = reinterpret_cast<uint32_t*>(rv_smem + (d & ~3u));
+    const uint32_t m_first = 0xFFFFFFFFu << (a * 8u);
+    const uint32_t e = (a + len) & 3u;
+    const uint32_t m_last = e ? (0xFFFFFFFFu >> ((4u - e) * 8u)) : 0xFFFFFFFFu;
+    uint32_t lo = sw[0], hi = sw[1];
+    uint32_t v = __funnelshift_r(lo, hi, sh);
+    if (nwords == 1u) {
+        atomicOr(dw, v & m_first & m_last);
+    } else {
+        atomicOr(dw, v & m_first);
+        uint32_t j = 1;
+        // (both loops are kept rolled: there are a dozen call sites per generated walker and real strings are a
+        // few words long, so unrolled copies only add code and branches — measured 5% slower on the emit kernel)
+#pragma unroll 1
+        for (; j + 4 < nwords; j += 4) {  // four interior words per trip
+            const uint32_t w1 = sw[j + 1], w2 = sw[j + 2], w3 = sw[j + 3], w4 = sw[j + 4];
+            dw[j] = __funnelshift_r(hi, w1, sh);
+            dw[j + 1] = __funnelshift_r(w1, w2, sh);
+            dw[j + 2] = __funnelshift_r(w2, w3, sh);
+            dw[j + 3] = __funnelshift_r(w3, w4, sh);
+            hi = w4;
+        }
+#pragma unroll 1
+        for (; j + 1 < nwords; ++j) {
+            lo = hi;
+            hi = sw[j + 1];
+            dw[j] = __funnelshift_r(lo, hi, sh);
+        }
+        lo = hi;
+        hi = sw[nwords];
+        atomicOr(dw + (nwords - 1u), __funnelshift_r(lo, hi, sh) & m_last);
+    }
+}
+#endif
+
 // ---- Utf8 leaves ----------------------------------------------------------------------------
 // Destination of string bytes: the CTA's shared-memory staging area (written out with coalesced
 // 128-bit stores by the kernel afterwards) or, when the tile does not fit, global memory directly.
@@ -258,45 +306,7 @@ RV_HD void copy_from_record(C& c, int slot_b, int stream, uint32_t o, uint32_t s
     if (c.stage_on) {
         const uint32_t d = c.stage_soff + c.stage_adj[stream] + o;
         if (C::kShared) {
-            // shared -> shared, one destination WORD per iteration (the warp's cost is its longest string,
-            // so iterations matter).  Destination word j takes 4 source bytes at an arbitrary alignment:
-            // two aligned source words + a funnel shift.  The first and last words are shared with the
-            // neighbouring strings (written by other lanes), so they are merged with atomicOr into the
-            // zero-initialised staging area; interior words are plain stores.  Source reads may touch up to
-            // 3 bytes before / 4 bytes after the string: still inside the CTA's shared memory.
-            const uint32_t a = d & 3u;
-            const uint32_t nwords = (a + len + 3u) >> 2;
-            const uint32_t sp = c.soff + s - a;  // source byte that lands in byte 0 of destination word 0
-            const uint32_t sh = (sp & 3u) * 8u;
-            const uint32_t* sw = reinterpret_cast<const uint32_t*>(rv_smem + (sp & ~3u));
-            uint32_t* dw = reinterpret_cast<uint32_t*>(rv_smem + (d & ~3u));
-            const uint32_t m_first = 0xFFFFFFFFu << (a * 8u);
-            const uint32_t e = (a + len) & 3u;
-            const uint32_t m_last = e ? (0xFFFFFFFFu >> ((4u - e) * 8u)) : 0xFFFFFFFFu;
-            uint32_t lo = sw[0], hi = sw[1];
-            uint32_t v = __funnelshift_r(lo, hi, sh);
-            if (nwords == 1u) {
-                atomicOr(dw, v & m_first & m_last);
-            } else {
-                atomicOr(dw, v & m_first);
-                uint32_t j = 1;
-                for (; j + 4 < nwords; j += 4) {  // four interior words per trip: the loop overhead dominates otherwise
-                    const uint32_t w1 = sw[j + 1], w2 = sw[j + 2], w3 = sw[j + 3], w4 = sw[j + 4];
-                    dw[j] = __funnelshift_r(hi, w1, sh);
-                    dw[j + 1] = __funnelshift_r(w1, w2, sh);
-                    dw[j + 2] = __funnelshift_r(w2, w3, sh);
-                    dw[j + 3] = __funnelshift_r(w3, w4, sh);
-                    hi = w4;
-                }
-                for (; j + 1 < nwords; ++j) {
-                    lo = hi;
-                    hi = sw[j + 1];
-                    dw[j] = __funnelshift_r(lo, hi, sh);
-                }
-                lo = hi;
-                hi = sw[nwords];
-                atomicOr(dw + (nwords - 1u), __funnelshift_r(lo, hi, sh) & m_last);
-            }
+            copy_smem_words(d, c.soff + s, len);
         } else {
             for (uint32_t i = 0; i < len; ++i) rv_smem[d + i] = uint8_t(ld_u8(c, s + i));
         }

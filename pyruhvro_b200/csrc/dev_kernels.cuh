@@ -208,39 +208,108 @@ __device__ __forceinline__ void count_body(const DecodeParams& p, const int tile
     __syncthreads();
     // CTA-wide exclusive scan of every stream's lane counts.  The per-record prefixes are saved so the
     // emit kernel does not have to walk the records a second time just to learn where they write.
+    // One WARP scans one stream: each lane takes 8 consecutive records (two 128-bit loads), sums them
+    // serially, and a single 5-step shuffle scan joins the 32 lane totals — instead of every warp running a
+    // shuffle scan per stream plus a cross-warp pass.
+    static_assert(kBlock == 256, "the tile scan assumes 32 lanes x 8 records");
     uint32_t* cur = reinterpret_cast<uint32_t*>(rv_smem + m.cur);
-    uint32_t* wtot = reinterpret_cast<uint32_t*>(rv_smem + m.wtot);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if constexpr (W::kRegCursors) {  // the scan area overlays the (now dead) input window
 #pragma unroll
         for (int s = 0; s < W::kStreams; ++s) cur[s * kBlock + tid] = q.v[s];
     }
-    for (int s = 0; s < p.n_streams; ++s) {
-        const uint32_t v = cur[s * kBlock + tid];
-        uint32_t incl = v;
+    __syncthreads();
+    for (int s = warp; s < p.n_streams; s += kWarps) {
+        uint32_t* c8 = cur + s * kBlock + lane * 8;
+        const uint4 a = *reinterpret_cast<const uint4*>(c8), b = *reinterpret_cast<const uint4*>(c8 + 4);
+        // 256 values below 2^23 cannot overflow 31 bits; anything bigger (a tile of huge zero-width lists) takes
+        // the exact 64-bit path below
+        const bool big = (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) >= (1u << 23);
+        if (__any_sync(0xFFFFFFFFu, big)) {
+            if (lane == 0) {
+                uint32_t* cs = cur + s * kBlock;
+                unsigned long long run = 0;
+                for (int i = 0; i < kBlock; ++i) {
+                    const uint32_t v = cs[i];
+                    cs[i] = uint32_t(run);
+                    run += v;
+                }
+                if (run > 0x7FFFFFFFull) { report(p, t.r0, E_OVERFLOW); run = 0x7FFFFFFFull; }
+                p.tile_agg[size_t(s) * p.n_tiles + tile_id] = uint32_t(run);
+            }
+            __syncwarp();
+            continue;
+        }
+        const uint32_t e1 = a.x, e2 = e1 + a.y, e3 = e2 + a.z, e4 = e3 + a.w;
+        const uint32_t e5 = e4 + b.x, e6 = e5 + b.y, e7 = e6 + b.z, tot = e7 + b.w;
+        uint32_t incl = tot;
+#pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
             if (lane >= d) incl += u;
         }
-        if (lane == 31) wtot[s * kWarps + warp] = incl;
-        cur[s * kBlock + tid] = incl - v;
-    }
-    __syncthreads();
-    // one thread per stream: exclusive prefix of the warp totals (in place) + the tile total
-    if (tid < p.n_streams) {
-        unsigned long long run = 0;
-        for (int ww = 0; ww < kWarps; ++ww) {
-            const uint32_t v = wtot[tid * kWarps + ww];
-            wtot[tid * kWarps + ww] = uint32_t(run);
-            run += v;
-        }
-        if (run > 0x7FFFFFFFull) { report(p, t.r0, E_OVERFLOW); run = 0x7FFFFFFFull; }
-        p.tile_agg[size_t(tid) * p.n_tiles + tile_id] = uint32_t(run);
+        const uint32_t base = incl - tot;
+        *reinterpret_cast<uint4*>(c8) = make_uint4(base, base + e1, base + e2, base + e3);
+        *reinterpret_cast<uint4*>(c8 + 4) = make_uint4(base + e4, base + e5, base + e6, base + e7);
+        if (lane == 31) p.tile_agg[size_t(s) * p.n_tiles + tile_id] = incl;  // < 2^31 by construction
     }
     __syncthreads();
     uint32_t* lo = p.lane_off + size_t(tile_id) * p.n_streams * kBlock;
-    for (int s = 0; s < p.n_streams; ++s) lo[s * kBlock + tid] = cur[s * kBlock + tid] + wtot[s * kWarps + warp];
+    if constexpr (W::kRegCursors) {
+#pragma unroll
+        for (int s = 0; s < W::kStreams; ++s) lo[s * kBlock + tid] = cur[s * kBlock + tid];
+    } else {
+        for (int s = 0; s < p.n_streams; ++s) lo[s * kBlock + tid] = cur[s * kBlock + tid];
+    }
     prefetch_window(p, w);
+}
+
+// ---- emit: staging map ------------------------------------------------------------------------
+// Stream s's Utf8 bytes of this tile occupy [tile_base, tile_base + tot) of its Arrow data buffer; in shared
+// memory its region starts at a 16-byte boundary plus the destination's misalignment, so the write-out can use
+// aligned uint4.  Warp 0 computes the map with a shuffle scan.  Its inputs do not depend on the tile's bytes, so
+// they are requested at the very top of the CTA (map_preload) and consumed after the window loads were issued
+// (map_finish): one barrier and one exposed L2 round trip less than computing the map after the window arrived.
+struct MapPre { uint32_t tb, tt, ga, region; int slot; };
+
+__device__ __forceinline__ MapPre map_preload(const DecodeParams& p, const Tile& t, const int tile_id, const int s) {
+    MapPre r{0u, 0u, 0u, 0u, -1};
+    if (s < p.n_streams) {
+        r.tb = __ldg(p.tile_base + size_t(s) * p.n_tiles + tile_id);
+        r.tt = __ldg(p.tile_agg + size_t(s) * p.n_tiles + tile_id);
+        r.slot = p.stream_slot[s];
+        if (r.slot >= 0) {
+            const uint8_t* b = static_cast<const uint8_t*>(p.bufs[size_t(t.chunk) * p.n_slots + r.slot]);
+            r.ga = uint32_t(reinterpret_cast<uintptr_t>(b + r.tb) & 15u);
+            r.region = (r.tt + r.ga + 15u) & ~15u;
+        }
+    }
+    return r;
+}
+
+// warp 0 only
+__device__ __forceinline__ void map_finish(const DecodeParams& p, const Tile& t, const int tile_id, const SmemMap& m, MapPre pre) {
+    uint32_t* tbase = reinterpret_cast<uint32_t*>(rv_smem + m.wtot);
+    uint32_t* tot = reinterpret_cast<uint32_t*>(rv_smem + m.tot);
+    uint32_t* adj = reinterpret_cast<uint32_t*>(rv_smem + m.adj);
+    const int lane = threadIdx.x & 31;
+    uint32_t carry = 0;
+    for (int s0 = 0; s0 < p.n_streams; s0 += 32) {
+        const int s = s0 + lane;
+        if (s0 > 0) pre = map_preload(p, t, tile_id, s);
+        uint32_t incl = pre.region;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += u;
+        }
+        if (s < p.n_streams) {
+            tbase[s] = pre.tb;
+            tot[s] = pre.tt;
+            adj[s] = pre.slot >= 0 ? (carry + incl - pre.region + pre.ga) - pre.tb : 0u;  // staging offset of chunk-relative byte o = adj + o
+        }
+        carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    if (lane == 0) tot[p.n_streams] = (p.smem_stage_cap > 0 && carry <= p.smem_stage_cap) ? 1u : 0u;
 }
 
 // ---- emit -----------------------------------------------------------------------------------
@@ -253,40 +322,8 @@ __device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t,
     uint32_t* adj = reinterpret_cast<uint32_t*>(rv_smem + m.adj);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // (each record's first row / first byte per stream was loaded into `cur` by stage_in: the chunk-relative
-    // tile base from scan_kernel + the record's prefix inside the tile from the count kernel)
-    // Staging map of the Utf8 streams, computed by warp 0 with a shuffle scan.  Stream s's bytes of this tile
-    // occupy [tile_base, tile_base + tot) of its Arrow data buffer; in shared memory its region starts at a
-    // 16-byte boundary plus the destination's misalignment, so the write-out can use aligned uint4.
-    if (warp == 0) {
-        uint32_t carry = 0;
-        for (int s0 = 0; s0 < p.n_streams; s0 += 32) {
-            const int s = s0 + lane;
-            uint32_t tb = 0, tt = 0, ga = 0, region = 0;
-            int slot = -1;
-            if (s < p.n_streams) {
-                tb = __ldg(p.tile_base + size_t(s) * p.n_tiles + tile_id);
-                tt = __ldg(p.tile_agg + size_t(s) * p.n_tiles + tile_id);
-                slot = p.stream_slot[s];
-                if (slot >= 0) {
-                    ga = uint32_t(reinterpret_cast<uintptr_t>(static_cast<uint8_t*>(buf_ptr(c, slot)) + tb) & 15u);
-                    region = (tt + ga + 15u) & ~15u;
-                }
-            }
-            uint32_t incl = region;
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= d) incl += u;
-            }
-            if (s < p.n_streams) {
-                tbase[s] = tb;
-                tot[s] = tt;
-                adj[s] = slot >= 0 ? (carry + incl - region + ga) - tb : 0u;  // staging offset of chunk-relative byte o = adj + o
-            }
-            carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
-        }
-        if (lane == 0) tot[p.n_streams] = (p.smem_stage_cap > 0 && carry <= p.smem_stage_cap) ? 1u : 0u;
-    }
-    __syncthreads();
+    // tile base from scan_kernel + the record's prefix inside the tile from the count kernel; the staging map
+    // was written by warp 0 before the barrier that published the window)
     const bool stage_on = p.n_streams > 0 && tot[p.n_streams] != 0;
     // offsets[0] = 0 of every offsets buffer of this chunk (first tile of the chunk only)
     if (t.local_tile == 0) {
@@ -330,7 +367,11 @@ __device__ __forceinline__ void emit_body(const DecodeParams& p, const int tile_
     const Tile t = tile_of(p, tile_id);
     const SmemMap m = smem_map(p.n_nodes, p.n_streams, p.n_slots, p.smem_data_cap, W::kRegCursors);
     typename W::Cur q;
+    const bool map_warp = threadIdx.x < 32;
+    MapPre pre{0u, 0u, 0u, 0u, -1};
+    if (map_warp) pre = map_preload(p, t, tile_id, int(threadIdx.x));
     const TileWindow w = stage_in<true, W>(p, t, tile_id, m, q);
+    if (map_warp) map_finish(p, t, tile_id, m, pre);
     __syncthreads();
     if (w.staged) emit_walks<W, true>(p, t, tile_id, m, w, q);
     else if constexpr (GENERIC) emit_walks<W, false>(p, t, tile_id, m, w, q);

@@ -149,6 +149,22 @@ def test_pipelined_chunks_large_batch(coracle, walker):
     assert "(record 20000)" in str(e.value) and "varint" in str(e.value)   # first failing chunk wins
 
 
+def test_huge_zero_width_lists_take_the_exact_tile_scan(coracle, walker):
+    """Arrays of `null` items cost no bytes per item, so a 256-record tile can hold > 2^31 rows: the count kernel's
+    tile scan switches to 64-bit arithmetic for such tiles (valid below the i32 ceiling, RV_ERR_OVERFLOW above)."""
+    sj = '{"type":"record","name":"Z","fields":[{"name":"a","type":{"type":"array","items":"null"}},{"name":"b","type":"long"}]}'
+    recs = [po.zigzag_bytes(1 << 23) + b"\x00" + po.zigzag_bytes(i) for i in range(64)]
+    data, off = po.pack_records(recs)
+    got = pr.deserialize_array_threaded(recs, sj, 1)
+    assert_matches_oracle(coracle, got, sj, data, off, len(recs), 1)
+    assert got[0].column("a").offsets[-1].as_py() == 64 << 23
+    bad = [po.zigzag_bytes(1 << 30) + b"\x00" + po.zigzag_bytes(i) for i in range(3)]
+    with pytest.raises(ValueError) as e:
+        pr.deserialize_array(bad, sj)
+    assert "overflow" in str(e.value)
+    assert pr.deserialize_array_threaded(bad, sj, 3)[2].column("a").offsets[-1].as_py() == 1 << 30
+
+
 def test_arrow_array_ingest_matches_list_ingest(coracle):
     """deserialize_arrow_array (Binary / LargeBinary / sliced / chunked) == deserialize_array_threaded on the list."""
     sj, recs, _, _ = gen_case(7, 300)

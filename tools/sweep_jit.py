@@ -37,8 +37,8 @@ def main():
     d_data[:total].copy_(torch.from_numpy(h_data))
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream()
-    names = [k.split("=")[0] for k in args.knobs]
-    values = [k.split("=")[1].split(",") for k in args.knobs]
+    names = [k.split("=", 1)[0] for k in args.knobs]
+    values = [k.split("=", 1)[1].split(",") for k in args.knobs]
     for combo in itertools.product(*values) if names else [()]:
         for k, v in zip(names, combo):
             os.environ[k] = v
