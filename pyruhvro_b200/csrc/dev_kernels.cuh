@@ -211,7 +211,7 @@ __device__ __forceinline__ void count_body(const DecodeParams& p, const int tile
     // One WARP scans one stream: each lane takes 8 consecutive records (two 128-bit loads), sums them
     // serially, and a single 5-step shuffle scan joins the 32 lane totals — instead of every warp running a
     // shuffle scan per stream plus a cross-warp pass.
-    static_assert(kBlock == 256, "the tile scan assumes 32 lanes x 8 records");
+    constexpr int kPerLane = kBlock / 32;  // 4, 8, ...: a multiple of 4, so every lane moves whole uint4
     uint32_t* cur = reinterpret_cast<uint32_t*>(rv_smem + m.cur);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if constexpr (W::kRegCursors) {  // the scan area overlays the (now dead) input window
@@ -220,19 +220,25 @@ __device__ __forceinline__ void count_body(const DecodeParams& p, const int tile
     }
     __syncthreads();
     for (int s = warp; s < p.n_streams; s += kWarps) {
-        uint32_t* c8 = cur + s * kBlock + lane * 8;
-        const uint4 a = *reinterpret_cast<const uint4*>(c8), b = *reinterpret_cast<const uint4*>(c8 + 4);
-        // 256 values below 2^23 cannot overflow 31 bits; anything bigger (a tile of huge zero-width lists) takes
-        // the exact 64-bit path below
-        const bool big = (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) >= (1u << 23);
-        if (__any_sync(0xFFFFFFFFu, big)) {
+        uint32_t* cl = cur + s * kBlock + lane * kPerLane;
+        uint32_t v[kPerLane];
+        uint32_t any = 0;
+#pragma unroll
+        for (int i = 0; i < kPerLane; i += 4) {
+            const uint4 x = *reinterpret_cast<const uint4*>(cl + i);
+            v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
+            any |= x.x | x.y | x.z | x.w;
+        }
+        // kBlock values below 2^31 / kBlock cannot overflow 31 bits; anything bigger (a tile of huge zero-width
+        // lists) takes the exact 64-bit path below
+        if (__any_sync(0xFFFFFFFFu, any >= (0x80000000u / uint32_t(kBlock)))) {
             if (lane == 0) {
                 uint32_t* cs = cur + s * kBlock;
                 unsigned long long run = 0;
                 for (int i = 0; i < kBlock; ++i) {
-                    const uint32_t v = cs[i];
+                    const uint32_t x = cs[i];
                     cs[i] = uint32_t(run);
-                    run += v;
+                    run += x;
                 }
                 if (run > 0x7FFFFFFFull) { report(p, t.r0, E_OVERFLOW); run = 0x7FFFFFFFull; }
                 p.tile_agg[size_t(s) * p.n_tiles + tile_id] = uint32_t(run);
@@ -240,8 +246,13 @@ __device__ __forceinline__ void count_body(const DecodeParams& p, const int tile
             __syncwarp();
             continue;
         }
-        const uint32_t e1 = a.x, e2 = e1 + a.y, e3 = e2 + a.z, e4 = e3 + a.w;
-        const uint32_t e5 = e4 + b.x, e6 = e5 + b.y, e7 = e6 + b.z, tot = e7 + b.w;
+        uint32_t tot = 0;
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) {  // lane-local exclusive prefix
+            const uint32_t x = v[i];
+            v[i] = tot;
+            tot += x;
+        }
         uint32_t incl = tot;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -249,8 +260,9 @@ __device__ __forceinline__ void count_body(const DecodeParams& p, const int tile
             if (lane >= d) incl += u;
         }
         const uint32_t base = incl - tot;
-        *reinterpret_cast<uint4*>(c8) = make_uint4(base, base + e1, base + e2, base + e3);
-        *reinterpret_cast<uint4*>(c8 + 4) = make_uint4(base + e4, base + e5, base + e6, base + e7);
+#pragma unroll
+        for (int i = 0; i < kPerLane; i += 4)
+            *reinterpret_cast<uint4*>(cl + i) = make_uint4(base + v[i], base + v[i + 1], base + v[i + 2], base + v[i + 3]);
         if (lane == 31) p.tile_agg[size_t(s) * p.n_tiles + tile_id] = incl;  // < 2^31 by construction
     }
     __syncthreads();

@@ -82,7 +82,11 @@ enum ErrCode : uint32_t {
     E_OVERFLOW = 8   // i32 Arrow offset overflow (arrow-rs panics; reported as an error)
 };
 
-constexpr int kBlock = 256;  // records per tile == threads per CTA (one record per lane)
+#ifndef RV_KBLOCK
+#define RV_KBLOCK 256
+#endif
+constexpr int kBlock = RV_KBLOCK;  // records per tile == threads per CTA (one record per lane)
+static_assert(kBlock % 128 == 0 && kBlock <= 1024, "tiles are whole groups of 4 warps");
 constexpr int kWarps = kBlock / 32;
 
 // Kernel parameter block (count / scan / emit).
