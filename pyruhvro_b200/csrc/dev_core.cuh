@@ -306,7 +306,9 @@ RV_HD void copy_from_record(C& c, int slot_b, int stream, uint32_t o, uint32_t s
     if (c.stage_on) {
         const uint32_t d = c.stage_soff + c.stage_adj[stream] + o;
         if (C::kShared) {
+#if !defined(RV_ABL_NOCOPY)  // (RV_ABL_*: timing ablations for tools/sweep_jit.py — they produce wrong output)
             copy_smem_words(d, c.soff + s, len);
+#endif
         } else {
             for (uint32_t i = 0; i < len; ++i) rv_smem[d + i] = uint8_t(ld_u8(c, s + i));
         }

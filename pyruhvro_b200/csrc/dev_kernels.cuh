@@ -47,6 +47,7 @@ __device__ __forceinline__ Tile tile_of(const DecodeParams& p, int tile) {
 
 struct TileWindow {
     bool staged;
+    bool tma;         // the window is in flight on the copy engine: wait_window() before reading it
     int64_t t0, t1;   // byte range of the tile in `data`
     uint32_t mis;     // (data + t0) & 15: the window starts at the aligned-down address
     int64_t o0, o1;   // this lane's record: byte range in `data`
@@ -61,12 +62,43 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) 
 }
 constexpr int kPrefetchLane = 32;  // the lane (first of warp 1) that carries the look-ahead
 
+// ---- TMA (bulk async copy) staging of the input window -----------------------------------------------
+// One thread hands the whole window to the copy engine (cp.async.bulk global -> shared, completion counted in
+// bytes on an mbarrier) instead of every thread moving its share through registers (LDG.128 + STS.128): the
+// prologue loses ~40 issue slots per thread and the loads no longer occupy registers.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+#if !defined(RV_NO_TMA_STAGE)
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "RV_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra RV_DONE;\n"
+        "bra RV_WAIT;\n"
+        "RV_DONE:\n"
+        "}" ::"r"(mbar), "r"(parity) : "memory");
+}
+#endif
+
 // Loads the plan and the tile's byte window into shared memory.
 // EMIT: the lanes' cursors (tile base + in-tile prefix) and, further down, zeroing of the Utf8 staging
 // area are issued here too, so their latency overlaps the input loads.
 template <bool EMIT, class W>
 __device__ __forceinline__ TileWindow stage_in(const DecodeParams& p, const Tile& t, const int tile_id, const SmemMap& m, typename W::Cur& q) {
     const int tid = threadIdx.x;
+#if !defined(RV_NO_TMA_STAGE)
+    if (tid == 0) mbar_init(smem_addr(rv_smem + m.mbar), 1);
+#endif
     if (p.n_nodes) {
         uint4* dn = reinterpret_cast<uint4*>(rv_smem + m.nodes);
         for (int i = tid; i < p.n_nodes * 2; i += kBlock) dn[i] = __ldg(reinterpret_cast<const uint4*>(p.nodes) + i);
@@ -117,13 +149,28 @@ __device__ __forceinline__ TileWindow stage_in(const DecodeParams& p, const Tile
     const int64_t span = w.t1 - w.t0;
     w.mis = uint32_t(reinterpret_cast<uintptr_t>(p.data + w.t0) & 15u);
     w.staged = span >= 0 && uint64_t(span) + w.mis <= uint64_t(p.smem_data_cap);
+    w.tma = false;
     if (w.staged) {
         const uint4* g = reinterpret_cast<const uint4*>(p.data + w.t0 - w.mis);
         const int nvec = int((span + w.mis + 15) >> 4);
         uint4* d = reinterpret_cast<uint4*>(rv_smem + m.in);
+#if !defined(RV_NO_TMA_STAGE)
+        w.tma = nvec > 0;
+        if (w.tma && tid == 0) bulk_load(smem_addr(d), g, uint32_t(nvec) << 4, smem_addr(rv_smem + m.mbar));
+#else
         for (int i = tid; i < nvec; i += kBlock) d[i] = __ldg(g + i);
+#endif
     }
     return w;
+}
+
+// After the CTA barrier that follows stage_in (which also publishes the mbarrier's initialisation).
+__device__ __forceinline__ void wait_window(const TileWindow& w, const SmemMap& m) {
+#if !defined(RV_NO_TMA_STAGE)
+    if (w.tma) mbar_wait(smem_addr(rv_smem + m.mbar), 0);
+#else
+    (void)w; (void)m;
+#endif
 }
 
 template <class C>
@@ -185,7 +232,9 @@ __device__ __forceinline__ void count_walk(const DecodeParams& p, const Tile& t,
 #pragma unroll
         for (int s = 0; s < W::kStreams; ++s) q.v[s] = 0;
     }
+#if !defined(RV_ABL_NOCOUNTWALK)
     W::template walk<WM_COUNT>(c, p.n_nodes, q);
+#endif
     if (c.in_range && c.err) report(p, r, c.err);
 }
 
@@ -199,6 +248,7 @@ __device__ __forceinline__ void count_body(const DecodeParams& p, const int tile
     typename W::Cur q;
     const TileWindow w = stage_in<false, W>(p, t, tile_id, m, q);
     __syncthreads();
+    wait_window(w, m);
     if (w.staged) count_walk<W, true>(p, t, m, w, q);
     else if constexpr (GENERIC) count_walk<W, false>(p, t, m, w, q);
     else {
@@ -350,10 +400,19 @@ __device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t,
         }
     }
     c.stage_on = stage_on;
+#if !defined(RV_ABL_NOWALK)
     W::template walk<WM_EMIT>(c, p.n_nodes, q);
+#endif
     prefetch_window(p, w);
 
+#if defined(RV_ABL_NOWRITEOUT)
+    if (false) {
+#else
     if (stage_on) {  // coalesced write-out of the staged Utf8 bytes, one warp per stream at a time
+#endif
+#if !defined(RV_NO_TMA_STORE)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staged bytes -> visible to the copy engine
+#endif
         __syncthreads();
         for (int s = warp; s < p.n_streams; s += kWarps) {
             const int slot = p.stream_slot[s];
@@ -365,12 +424,26 @@ __device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t,
             const uint32_t head = min(n, (16u - uint32_t(reinterpret_cast<uintptr_t>(g) & 15u)) & 15u);
             for (uint32_t i = lane; i < head; i += 32) g[i] = rv_smem[so + i];
             const uint32_t nvec = (n - head) >> 4;
+#if !defined(RV_NO_TMA_STORE)
+            // the 16-byte aligned body leaves through the copy engine (shared -> global bulk store): one
+            // instruction per column instead of a store loop, and the warp does not wait for the data to drain
+            if (lane == 0 && nvec > 0)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(g + head), "r"(smem_addr(rv_smem + so + head)), "r"(nvec << 4) : "memory");
+#else
             const uint4* sv = reinterpret_cast<const uint4*>(rv_smem + so + head);
             uint4* gv = reinterpret_cast<uint4*>(g + head);
             for (uint32_t i = lane; i < nvec; i += 32) gv[i] = sv[i];
+#endif
             const uint32_t done = head + (nvec << 4);
             for (uint32_t i = done + lane; i < n; i += 32) g[i] = rv_smem[so + i];
         }
+#if !defined(RV_NO_TMA_STORE)
+        if (lane == 0) {  // shared memory must outlive the engine's reads
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+#endif
     }
 }
 
@@ -385,6 +458,7 @@ __device__ __forceinline__ void emit_body(const DecodeParams& p, const int tile_
     const TileWindow w = stage_in<true, W>(p, t, tile_id, m, q);
     if (map_warp) map_finish(p, t, tile_id, m, pre);
     __syncthreads();
+    wait_window(w, m);
     if (w.staged) emit_walks<W, true>(p, t, tile_id, m, w, q);
     else if constexpr (GENERIC) emit_walks<W, false>(p, t, tile_id, m, w, q);
     // else: the tile is on the overflow list and the interpreter pass emits it

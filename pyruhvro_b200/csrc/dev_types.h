@@ -130,7 +130,7 @@ struct DecodeParams {
 // alias_cur (walkers that keep their cursors in registers): the scan area `cur` overlays the input window
 // (it is only written after every lane finished reading the window) and costs no extra shared memory.
 struct SmemMap {
-    uint32_t nodes, wtot, tot, adj, ptrs, cur, in, out;
+    uint32_t nodes, wtot, tot, adj, mbar, ptrs, cur, in, out;
 };
 
 #if defined(__CUDACC__)
@@ -142,7 +142,8 @@ inline SmemMap smem_map(int n_nodes, int n_streams, int n_slots, uint32_t data_c
     m.wtot = uint32_t(n_nodes) * 32u;
     m.tot = m.wtot + uint32_t(n_streams) * kWarps * 4u;
     m.adj = m.tot + uint32_t(n_streams + 1) * 4u;
-    m.ptrs = (m.adj + uint32_t(n_streams) * 4u + 15u) & ~15u;
+    m.mbar = (m.adj + uint32_t(n_streams) * 4u + 7u) & ~7u;  // mbarrier of the bulk-copy staging (8 bytes)
+    m.ptrs = (m.mbar + 8u + 15u) & ~15u;
     m.cur = (m.ptrs + uint32_t(n_slots) * 8u + 15u) & ~15u;
     const uint32_t cur_bytes = uint32_t(n_streams) * kBlock * 4u;
     if (alias_cur) {

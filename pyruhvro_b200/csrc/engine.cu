@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -406,6 +407,16 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
 
     for (int i = 0; i < 4; ++i) t_timings[i] = 0;
     t_launches = 0;
+    // RV_TRACE=1: host-side phase times of this call on stderr (development aid)
+    static const bool trace = std::getenv("RV_TRACE") && std::getenv("RV_TRACE")[0] == '1';
+    auto t_prev = std::chrono::steady_clock::now();
+    std::string trace_line;
+    auto mark = [&](const char* what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        trace_line += std::string(what) + "=" + std::to_string(std::chrono::duration<double, std::micro>(now - t_prev).count()).substr(0, 6) + "us ";
+        t_prev = now;
+    };
 
     std::vector<unsigned long long> chunk_tot(size_t(k) * size_t(std::max(S, 1)), 0ull);
     DecodeParams p{};
@@ -420,6 +431,7 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
     bool use_jit = false;
     cudaKernel_t jit_count = nullptr, jit_emit = nullptr;
 
+    mark("setup");
     if (n > 0) {
         DevicePlan dp;
         rv_status st = device_plan(s, device, &dp);
@@ -449,6 +461,7 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
             RV_CUDA(cudaStreamSynchronize(stream));
             if (total_bytes < 0) total_bytes = ends[1] - ends[0];
         }
+        mark("span_sync");
         // Walker: schema-specialised (NVRTC) when available, else the generic interpreter.
         const JitState& jit = ensure_jit(s, device);
         use_jit = jit.ok;
@@ -501,6 +514,7 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         p.bufs = nullptr;
         RV_CUDA(cudaMemsetAsync(d_err.p, 0xFF, 8, stream));
 
+        mark("allocs");
         RV_CUDA(cudaEventRecord(ev[0], stream));
         p.tile_list = nullptr;
         p.overflow = static_cast<int32_t*>(d_overflow.p);
@@ -532,7 +546,9 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         RV_CUDA(cudaMemcpyAsync(&err_word, d_err.p, 8, cudaMemcpyDeviceToHost, stream));
         RV_CUDA(cudaMemcpyAsync(&max_utf8, static_cast<unsigned long long*>(d_stats.p) + 1, 8, cudaMemcpyDeviceToHost, stream));
         if (S > 0) RV_CUDA(cudaMemcpyAsync(chunk_tot.data(), d_chunk_tot.p, chunk_tot.size() * 8, cudaMemcpyDeviceToHost, stream));
+        mark("count_launched");
         RV_CUDA(cudaStreamSynchronize(stream));
+        mark("count_sync");
         t_overflow_tiles = overflow_n;
         if (err_word != ~0ull) {
             const uint32_t code = uint32_t(err_word & 0xFF);
@@ -589,6 +605,7 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
                 p.prefetch_dist = sms * int(std::max<size_t>(1, std::min<size_t>(8, (228 * 1024) / (smem_emit + 1024))));
             }
         }
+        mark("layout");
         RV_CUDA(cudaEventRecord(ev[3], stream));
         if (use_jit) {
             void* args[] = {&p};
@@ -628,7 +645,9 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         } else {
             RV_CUDA(cudaEventRecord(ev[5], stream));
         }
+        mark("emit_launched");
         RV_CUDA(cudaStreamSynchronize(stream));
+        mark("emit_sync");
         for (int j = 0; j < k; ++j)
             for (int v = 0; v < nv; ++v) {
                 const int sl = plan.validity_slots[size_t(v)];
@@ -645,6 +664,8 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         RV_CUDA(cudaStreamSynchronize(stream));
     }
     res->arrow_bytes = exported_bytes(plan, res->chunks);
+    mark("finish");
+    if (trace) std::fprintf(stderr, "[rv trace] %s\n", trace_line.c_str());
     *out = res.release();
     return RV_OK;
 }
