@@ -252,7 +252,7 @@ __device__ __forceinline__ void count_body(const DecodeParams& p, const int tile
     if (w.staged) count_walk<W, true>(p, t, m, w, q);
     else if constexpr (GENERIC) count_walk<W, false>(p, t, m, w, q);
     else {
-        if (threadIdx.x == 0) p.overflow[1 + atomicAdd(p.overflow, 1)] = tile_id;
+        if (threadIdx.x == 0) p.overflow_list[atomicAdd(p.overflow, 1)] = tile_id;
         return;  // uniform: the whole CTA leaves
     }
     __syncthreads();

@@ -387,6 +387,44 @@ const char* err_text(uint32_t code) {
     }
 }
 
+// Small pinned host block per calling thread: the template the control words are initialised from and the
+// landing zone of their read-back.  (Copies to pageable memory block the host once per copy; a decode call used
+// to make eight of them.)
+struct HostScratch {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    uint8_t* get(size_t bytes) {
+        if (bytes > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            cap = 0;
+            const size_t want = std::max<size_t>(bytes * 2, 1 << 16);
+            if (cudaHostAlloc(reinterpret_cast<void**>(&p), want, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); p = nullptr; return nullptr; }
+            cap = want;
+        }
+        return p;
+    }
+};
+thread_local HostScratch t_scratch;
+
+struct EventPool {  // cudaEventCreate/Destroy per call is measurable at small batch sizes
+    cudaEvent_t ev[8] = {};
+    int device = -1;
+    cudaError_t get(int dev, cudaEvent_t** out) {
+        if (device != dev) {
+            for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+            for (auto& e : ev) { const cudaError_t r = cudaEventCreate(&e); if (r != cudaSuccess) return r; }
+            device = dev;
+        }
+        *out = ev;
+        return cudaSuccess;
+    }
+};
+thread_local EventPool t_events;
+
+// device control block of one decode call, in 64-bit words
+enum CtrlWord : int { CW_ERR = 0, CW_MAX_SPAN = 1, CW_MAX_UTF8 = 2, CW_OVERFLOW = 3, CW_OFF_FIRST = 4, CW_OFF_LAST = 5, CW_CHUNK_TOT = 8 };
+
 // ---- the decode call ------------------------------------------------------------------------
 rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d_offsets, int64_t n, int64_t num_chunks,
                            int64_t total_bytes_hint, cudaStream_t stream, int device, rv_result** out, int64_t record_base = 0) {
@@ -420,12 +458,13 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
 
     std::vector<unsigned long long> chunk_tot(size_t(k) * size_t(std::max(S, 1)), 0ull);
     DecodeParams p{};
-    DevBuf tile_agg, tile_base, lane_off, d_chunk_tot, d_err, d_bufs, d_overflow, d_stats;
+    DevBuf tile_agg, tile_base, lane_off, d_ctrl, d_bufs, d_overflow;
     DecodeParams pi{};   // interpreter pass over the tiles the specialised kernels skipped
     size_t smem_interp = 0;
-    cudaEvent_t ev[8];
-    for (auto& e : ev) RV_CUDA(cudaEventCreate(&e));
-    struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 8; ++i) cudaEventDestroy(e[i]); } } evg{ev};
+    cudaEvent_t* ev = nullptr;
+    RV_CUDA(t_events.get(device, &ev));
+    const size_t ctrl_words = size_t(CW_CHUNK_TOT) + chunk_tot.size();
+    unsigned long long* h_ctrl = nullptr;  // pinned: [template][read-back]
     size_t smem_count = 0, smem_emit = 0, smem_room_out = 0;
     unsigned long long max_utf8 = 0;
     bool use_jit = false;
@@ -444,23 +483,25 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         // tiling is known: fill it in first so the sizing kernel can use it
         p.data = d_data; p.offsets = d_offsets; p.n = n; p.chunk_rows = chunk_rows; p.k = k;
         p.tiles_per_chunk = int32_t(tpc); p.n_tiles = int32_t(n_tiles);
-        RV_CUDA(d_stats.alloc(16, stream));
-        RV_CUDA(cudaMemsetAsync(d_stats.p, 0, 16, stream));
-        launch_tile_span_max(p, static_cast<unsigned long long*>(d_stats.p), stream);
+        // control block: error word, window maxima, overflow count, input span, per-chunk stream totals —
+        // initialised by ONE copy from the pinned template and read back by one copy per phase
+        const size_t ones_words = size_t(k) * std::max<size_t>(plan.validity_slots.size(), 1);
+        h_ctrl = reinterpret_cast<unsigned long long*>(t_scratch.get((ctrl_words * 2 + ones_words) * 8));
+        if (!h_ctrl) return fail(RV_ERR_CUDA, "pinned allocation of the control block failed");
+        unsigned long long* h_back = h_ctrl + ctrl_words;
+        std::memset(h_ctrl, 0, ctrl_words * 8);
+        h_ctrl[CW_ERR] = ~0ull;
+        RV_CUDA(d_ctrl.alloc(ctrl_words * 8, stream));
+        unsigned long long* ctrl = static_cast<unsigned long long*>(d_ctrl.p);
+        RV_CUDA(cudaMemcpyAsync(ctrl, h_ctrl, ctrl_words * 8, cudaMemcpyHostToDevice, stream));
+        launch_tile_span_max(p, ctrl, stream);  // CW_MAX_SPAN, CW_OFF_FIRST, CW_OFF_LAST
         RV_CUDA(cudaGetLastError());
         t_launches += 1;
-        unsigned long long max_span = 0;
+        RV_CUDA(cudaMemcpyAsync(h_back, ctrl, size_t(CW_CHUNK_TOT) * 8, cudaMemcpyDeviceToHost, stream));
+        RV_CUDA(cudaStreamSynchronize(stream));
+        const unsigned long long max_span = h_back[CW_MAX_SPAN];
         int64_t total_bytes = total_bytes_hint;
-        {
-            int64_t ends[2] = {0, 0};
-            RV_CUDA(cudaMemcpyAsync(&max_span, d_stats.p, 8, cudaMemcpyDeviceToHost, stream));
-            if (total_bytes < 0) {
-                RV_CUDA(cudaMemcpyAsync(&ends[0], d_offsets, 8, cudaMemcpyDeviceToHost, stream));
-                RV_CUDA(cudaMemcpyAsync(&ends[1], d_offsets + n, 8, cudaMemcpyDeviceToHost, stream));
-            }
-            RV_CUDA(cudaStreamSynchronize(stream));
-            if (total_bytes < 0) total_bytes = ends[1] - ends[0];
-        }
+        if (total_bytes < 0) total_bytes = int64_t(h_back[CW_OFF_LAST]) - int64_t(h_back[CW_OFF_FIRST]);
         mark("span_sync");
         // Walker: schema-specialised (NVRTC) when available, else the generic interpreter.
         const JitState& jit = ensure_jit(s, device);
@@ -502,28 +543,25 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         RV_CUDA(tile_agg.alloc(size_t(std::max(S, 1)) * size_t(n_tiles) * 4, stream));
         RV_CUDA(tile_base.alloc(size_t(std::max(S, 1)) * size_t(n_tiles) * 4, stream));
         RV_CUDA(lane_off.alloc(size_t(std::max(S, 1)) * size_t(n_tiles) * kBlock * 4, stream));
-        RV_CUDA(d_chunk_tot.alloc(chunk_tot.size() * 8, stream));
-        RV_CUDA(d_err.alloc(8, stream));
         RV_CUDA(d_overflow.alloc((size_t(n_tiles) + 1) * 4, stream));
-        RV_CUDA(cudaMemsetAsync(d_overflow.p, 0, 4, stream));
         p.tile_agg = static_cast<uint32_t*>(tile_agg.p);
         p.tile_base = static_cast<uint32_t*>(tile_base.p);
         p.lane_off = static_cast<uint32_t*>(lane_off.p);
-        p.chunk_tot = static_cast<unsigned long long*>(d_chunk_tot.p);
-        p.err = static_cast<unsigned long long*>(d_err.p);
+        p.chunk_tot = ctrl + CW_CHUNK_TOT;
+        p.err = ctrl + CW_ERR;
         p.bufs = nullptr;
-        RV_CUDA(cudaMemsetAsync(d_err.p, 0xFF, 8, stream));
 
         mark("allocs");
         RV_CUDA(cudaEventRecord(ev[0], stream));
         p.tile_list = nullptr;
-        p.overflow = static_cast<int32_t*>(d_overflow.p);
+        p.overflow = reinterpret_cast<int32_t*>(ctrl + CW_OVERFLOW);
+        p.overflow_list = static_cast<int32_t*>(d_overflow.p);
         if (use_jit) {
             void* args[] = {&p};
             RV_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(jit_count), dim3(unsigned(p.n_tiles)), dim3(kBlock), args, smem_count, stream));
             pi = p;
             pi.n_nodes = int32_t(plan.nodes.size());
-            pi.tile_list = static_cast<const int32_t*>(d_overflow.p) + 1;
+            pi.tile_list = static_cast<const int32_t*>(d_overflow.p);
             pi.smem_stage_cap = 0;
             pi.smem_data_cap = uint32_t(std::min<size_t>(cap_in, (limit - smem_map(pi.n_nodes, S, n_slots, 0, false).in - 64) & ~size_t(15)));
             smem_interp = smem_map(pi.n_nodes, S, n_slots, pi.smem_data_cap, false).out;
@@ -535,20 +573,19 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         RV_CUDA(cudaEventRecord(ev[1], stream));
         launch_scan(p, stream);
         RV_CUDA(cudaEventRecord(ev[2], stream));
-        launch_tile_utf8_max(p, static_cast<unsigned long long*>(d_stats.p) + 1, stream);
+        launch_tile_utf8_max(p, ctrl + CW_MAX_UTF8, stream);
         t_launches += 1;
         RV_CUDA(cudaGetLastError());
         t_launches += S > 0 ? 2 : 1;
 
-        unsigned long long err_word = ~0ull;
-        int overflow_n = 0;
-        RV_CUDA(cudaMemcpyAsync(&overflow_n, d_overflow.p, 4, cudaMemcpyDeviceToHost, stream));
-        RV_CUDA(cudaMemcpyAsync(&err_word, d_err.p, 8, cudaMemcpyDeviceToHost, stream));
-        RV_CUDA(cudaMemcpyAsync(&max_utf8, static_cast<unsigned long long*>(d_stats.p) + 1, 8, cudaMemcpyDeviceToHost, stream));
-        if (S > 0) RV_CUDA(cudaMemcpyAsync(chunk_tot.data(), d_chunk_tot.p, chunk_tot.size() * 8, cudaMemcpyDeviceToHost, stream));
+        RV_CUDA(cudaMemcpyAsync(h_back, ctrl, ctrl_words * 8, cudaMemcpyDeviceToHost, stream));
         mark("count_launched");
         RV_CUDA(cudaStreamSynchronize(stream));
         mark("count_sync");
+        const unsigned long long err_word = h_back[CW_ERR];
+        const int overflow_n = int(uint32_t(h_back[CW_OVERFLOW]));
+        max_utf8 = h_back[CW_MAX_UTF8];
+        std::memcpy(chunk_tot.data(), h_back + CW_CHUNK_TOT, chunk_tot.size() * 8);
         t_overflow_tiles = overflow_n;
         if (err_word != ~0ull) {
             const uint32_t code = uint32_t(err_word & 0xFF);
@@ -641,13 +678,14 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
             RV_CUDA(cudaGetLastError());
             t_launches += 1;
             RV_CUDA(cudaEventRecord(ev[5], stream));
-            RV_CUDA(cudaMemcpyAsync(ones.data(), d_ones.p, ones.size() * 8, cudaMemcpyDeviceToHost, stream));
+            RV_CUDA(cudaMemcpyAsync(h_ctrl + ctrl_words * 2, d_ones.p, ones.size() * 8, cudaMemcpyDeviceToHost, stream));
         } else {
             RV_CUDA(cudaEventRecord(ev[5], stream));
         }
         mark("emit_launched");
         RV_CUDA(cudaStreamSynchronize(stream));
         mark("emit_sync");
+        if (nv > 0) std::memcpy(ones.data(), h_ctrl + ctrl_words * 2, ones.size() * 8);
         for (int j = 0; j < k; ++j)
             for (int v = 0; v < nv; ++v) {
                 const int sl = plan.validity_slots[size_t(v)];

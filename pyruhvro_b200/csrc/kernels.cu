@@ -111,7 +111,13 @@ __global__ void null_count_kernel(const NullCountJob* jobs, long long* ones_out)
 
 // ---- window sizing: the largest tile decides how much shared memory a CTA needs ---------------------
 // max over tiles of the tile's input byte span (one thread per tile).
-__global__ void tile_span_max_kernel(const DecodeParams p, unsigned long long* out_max) {
+// Also notes the first and last input offset (the input's byte span) in the control block.
+__global__ void tile_span_max_kernel(const DecodeParams p, unsigned long long* ctrl) {
+    unsigned long long* out_max = ctrl + 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctrl[4] = static_cast<unsigned long long>(p.offsets[0]);
+        ctrl[5] = static_cast<unsigned long long>(p.offsets[p.n]);
+    }
     unsigned long long m = 0;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < p.n_tiles; t += gridDim.x * blockDim.x) {
         const Tile tl = tile_of(p, t);
@@ -167,9 +173,9 @@ __global__ void concat_bits_kernel(uint32_t* dst, long long dst_bit, const uint3
 
 }  // namespace
 
-void launch_tile_span_max(const DecodeParams& p, unsigned long long* out_max, cudaStream_t s) {
+void launch_tile_span_max(const DecodeParams& p, unsigned long long* ctrl, cudaStream_t s) {
     const int blocks = std::max(1, std::min((p.n_tiles + 255) / 256, 148 * 4));
-    tile_span_max_kernel<<<blocks, 256, 0, s>>>(p, out_max);
+    tile_span_max_kernel<<<blocks, 256, 0, s>>>(p, ctrl);
 }
 
 void launch_tile_utf8_max(const DecodeParams& p, unsigned long long* out_max, cudaStream_t s) {
