@@ -157,6 +157,9 @@ RV_HD bool rd_branch(C& c, bool null_first) {
 // bits go through atomicOr into a zero-initialised buffer.
 template <int D, class C>
 RV_HD void put_bit(C& c, int slot, uint32_t row, bool bit) {
+#if defined(RV_ABL_NOBITS)
+    return;
+#endif
 #if defined(__CUDA_ARCH__)
     if (D == 0) {
         const unsigned w = __ballot_sync(0xFFFFFFFFu, bit);
@@ -170,7 +173,15 @@ RV_HD void put_bit(C& c, int slot, uint32_t row, bool bit) {
 }
 
 template <int D, class C>
-RV_HD bool may_store(const C& c) { return (D > 0) || c.in_range; }
+RV_HD bool may_store(const C& c) {
+#if defined(RV_ABL_NOSTORE)
+    return false;
+#elif defined(RV_ABL_NOSTORE_DEEP)
+    return D == 0 && c.in_range;
+#else
+    return (D > 0) || c.in_range;
+#endif
+}
 
 // ---- fixed-width leaves -------------------------------------------------------------------
 template <int MODE, int D, class C>

@@ -466,6 +466,7 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
     const size_t ctrl_words = size_t(CW_CHUNK_TOT) + chunk_tot.size();
     unsigned long long* h_ctrl = nullptr;  // pinned: [template][read-back]
     size_t smem_count = 0, smem_emit = 0, smem_room_out = 0;
+    const size_t pad_count = size_t(env_double("RV_COUNT_SMEM_PAD", 0)), pad_emit = size_t(env_double("RV_EMIT_SMEM_PAD", 0));
     unsigned long long max_utf8 = 0;
     bool use_jit = false;
     cudaKernel_t jit_count = nullptr, jit_emit = nullptr;
@@ -552,6 +553,8 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         p.bufs = nullptr;
 
         mark("allocs");
+        // development knobs: extra (unused) dynamic shared memory per CTA, to measure the kernels' sensitivity to occupancy
+        smem_count = std::min<size_t>(smem_count + pad_count, limit);
         RV_CUDA(cudaEventRecord(ev[0], stream));
         p.tile_list = nullptr;
         p.overflow = reinterpret_cast<int32_t*>(ctrl + CW_OVERFLOW);
@@ -635,7 +638,7 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
             }
             if (const char* ev_ = std::getenv("RV_NO_STAGE_OUT")) if (ev_[0] == '1') cap_out = 0;
             p.smem_stage_cap = uint32_t(cap_out);
-            smem_emit = smem_count + cap_out;
+            smem_emit = std::min<size_t>(smem_count - pad_count + cap_out + pad_emit, 227 * 1024);
             if (p.prefetch_dist > 0) {
                 int sms = 148;
                 cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
