@@ -97,6 +97,9 @@ RV_HD int64_t rd_varint(C& c) {
     }
     uint64_t r = 0;
     uint32_t shift = 0;
+#if defined(__CUDACC__) && defined(RV_VARINT_ROLLED)
+#pragma unroll 1
+#endif
     for (;;) {
         if (CHECK && c.pos >= c.end) { fail(c, E_EOF); return 0; }
         const uint32_t b = ld_u8(c, c.pos++);
@@ -311,10 +314,16 @@ __device__ __forceinline__ void copy_smem_words(const uint32_t d, const uint32_t
 // ---- Utf8 leaves ----------------------------------------------------------------------------
 // Destination of string bytes: the CTA's shared-memory staging area (written out with coalesced
 // 128-bit stores by the kernel afterwards) or, when the tile does not fit, global memory directly.
+// RV_EMIT_STAGED_ONLY (set by the generated kernels): the walker is only ever run on tiles whose strings fit
+// the staging area — emit_body hands the others to the interpreter pass — so the fallback is compiled out.
 template <class C>
 RV_HD void copy_from_record(C& c, int slot_b, int stream, uint32_t o, uint32_t s, uint32_t len) {
 #if defined(__CUDA_ARCH__)
+#if defined(RV_EMIT_STAGED_ONLY)
+    if (true) {
+#else
     if (c.stage_on) {
+#endif
         const uint32_t d = c.stage_soff + c.stage_adj[stream] + o;
         if (C::kShared) {
 #if !defined(RV_ABL_NOCOPY)  // (RV_ABL_*: timing ablations for tools/sweep_jit.py — they produce wrong output)
@@ -334,7 +343,11 @@ RV_HD void copy_from_record(C& c, int slot_b, int stream, uint32_t o, uint32_t s
 template <class C>
 RV_HD void copy_from_symbols(C& c, int slot_b, int stream, uint32_t o, const uint8_t* src, uint32_t len) {
 #if defined(__CUDA_ARCH__)
+#if defined(RV_EMIT_STAGED_ONLY)
+    if (true) {
+#else
     if (c.stage_on) {
+#endif
         const uint32_t d = c.stage_soff + c.stage_adj[stream] + o;
         for (uint32_t i = 0; i < len; ++i) rv_smem[d + i] = src[i];
         return;

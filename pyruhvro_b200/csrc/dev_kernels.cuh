@@ -459,9 +459,20 @@ __device__ __forceinline__ void emit_body(const DecodeParams& p, const int tile_
     if (map_warp) map_finish(p, t, tile_id, m, pre);
     __syncthreads();
     wait_window(w, m);
-    if (w.staged) emit_walks<W, true>(p, t, tile_id, m, w, q);
-    else if constexpr (GENERIC) emit_walks<W, false>(p, t, tile_id, m, w, q);
-    // else: the tile is on the overflow list and the interpreter pass emits it
+    if constexpr (!GENERIC) {
+        // specialised walker: staged input AND staged output only.  (!w.staged: the count pass already put the
+        // tile on the overflow list.)
+        if (!w.staged) return;
+        const uint32_t* tot = reinterpret_cast<const uint32_t*>(rv_smem + m.tot);
+        if (p.n_utf8 > 0 && tot[p.n_streams] == 0) {
+            if (threadIdx.x == 0) p.overflow_list[atomicAdd(p.overflow, 1)] = tile_id;
+            return;  // uniform
+        }
+        emit_walks<W, true>(p, t, tile_id, m, w, q);
+    } else {
+        if (w.staged) emit_walks<W, true>(p, t, tile_id, m, w, q);
+        else emit_walks<W, false>(p, t, tile_id, m, w, q);
+    }
 }
 
 }  // namespace rv

@@ -119,7 +119,9 @@ struct DecodeParams {
     // bytes fit the shared-memory window; they append the others to `overflow_list` (`overflow[0]` counts them) and the generic interpreter kernels are launched over that list (tile_list != nullptr).
     const int32_t* tile_list;  // interpreter pass over overflow tiles: blockIdx.x -> tile id
     int32_t* overflow;         // specialised count pass: number of tiles it skipped ...
-    int32_t* overflow_list;    // ... and their ids
+    int32_t* overflow_list;    // ... and their ids (the specialised emit pass appends tiles whose strings do not fit
+                               // its staging area; the interpreter emit pass handles both kinds)
+    int32_t n_utf8;            // Utf8 byte streams in the plan
     int32_t prefetch_dist;    // CTAs resident on the device: a CTA prefetches (into L2) the tile that far ahead
     uint32_t smem_data_cap;   // bytes of shared memory for staging a tile's input bytes
     uint32_t smem_stage_cap;  // bytes of shared memory for staging a tile's Utf8 output bytes (emit)

@@ -531,6 +531,8 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         const int n_nodes_param = plan_nodes;
         p.nodes = dp.nodes; p.n_nodes = int32_t(n_nodes_param); p.n_streams = S; p.n_slots = n_slots;
         p.sym_off = dp.sym_off; p.sym_bytes = dp.sym_bytes;
+        p.n_utf8 = 0;
+        for (int st_ = 0; st_ < S; ++st_) p.n_utf8 += plan.streams[size_t(st_)].is_rows ? 0 : 1;
         p.smem_data_cap = uint32_t(cap_in);
         p.prefetch_dist = 0;
         if (!(std::getenv("RV_NO_PREFETCH") && std::getenv("RV_NO_PREFETCH")[0] == '1')) {
@@ -634,7 +636,7 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
                 cap_out = std::min<size_t>(size_t(max_utf8), size_t(per_tile * env_double("RV_OUT_CLAMP", 1.5)) + size_t(n_utf8) * 31) + 64;
                 cap_out = (cap_out + 63) & ~size_t(63);
                 if (cap_out > smem_room_out) cap_out = smem_room_out & ~size_t(15);
-                if (cap_out < 1024) cap_out = 0;
+                if (cap_out < 256) cap_out = 0;  // no room at all: strings go straight to global (interpreter pass)
             }
             if (const char* ev_ = std::getenv("RV_NO_STAGE_OUT")) if (ev_[0] == '1') cap_out = 0;
             p.smem_stage_cap = uint32_t(cap_out);
@@ -685,9 +687,12 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         } else {
             RV_CUDA(cudaEventRecord(ev[5], stream));
         }
+        // the overflow counter again: the specialised emit pass may have added tiles whose strings did not fit
+        if (use_jit) RV_CUDA(cudaMemcpyAsync(h_ctrl + ctrl_words, d_ctrl.p ? static_cast<unsigned long long*>(d_ctrl.p) + CW_OVERFLOW : nullptr, 8, cudaMemcpyDeviceToHost, stream));
         mark("emit_launched");
         RV_CUDA(cudaStreamSynchronize(stream));
         mark("emit_sync");
+        if (use_jit) t_overflow_tiles = int(uint32_t(h_ctrl[ctrl_words]));
         if (nv > 0) std::memcpy(ones.data(), h_ctrl + ctrl_words * 2, ones.size() * 8);
         for (int j = 0; j < k; ++j)
             for (int v = 0; v < nv; ++v) {

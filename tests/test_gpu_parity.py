@@ -247,6 +247,25 @@ def test_error_surface():
         pr.deserialize_array([b""], "{not json")
 
 
+def test_specialised_emit_hands_unstageable_tiles_to_the_interpreter(coracle, monkeypatch):
+    """The generated emit kernel only runs tiles whose strings fit its staging area; with the staging area clamped
+    below the largest tile (RV_OUT_CLAMP) the rest must come out right through the interpreter's emit pass."""
+    import workloads
+    sj, data, off = workloads.generate("kafka", 60_000, seed=5)
+    pr.set_jit_enabled(1)
+    try:
+        monkeypatch.setenv("RV_OUT_CLAMP", "1.0")
+        got = pr.decode_packed(data, off, 60_000, sj, 3)
+        assert pr.last_walker() == "jit" and pr.lib.rv_last_overflow_tiles() > 0
+        assert_matches_oracle(coracle, got, sj, data, off, 60_000, 3)
+        monkeypatch.setenv("RV_IN_CLAMP", "1.0")     # and with the input window clamped too (count-phase overflow)
+        got = pr.decode_packed(data, off, 60_000, sj, 3)
+        assert pr.lib.rv_last_overflow_tiles() > 0
+        assert_matches_oracle(coracle, got, sj, data, off, 60_000, 3)
+    finally:
+        pr.set_jit_enabled(-1)
+
+
 def test_large_records_use_global_path(coracle, walker):
     """Records far larger than the shared-memory tile exercise the direct-from-global walk; under the
     specialised kernels those tiles are routed to the interpreter kernels through the overflow list."""
