@@ -97,9 +97,6 @@ RV_HD int64_t rd_varint(C& c) {
     }
     uint64_t r = 0;
     uint32_t shift = 0;
-#if defined(__CUDACC__) && defined(RV_VARINT_ROLLED)
-#pragma unroll 1
-#endif
     for (;;) {
         if (CHECK && c.pos >= c.end) { fail(c, E_EOF); return 0; }
         const uint32_t b = ld_u8(c, c.pos++);
