@@ -58,6 +58,23 @@ def test_columns_matched_by_name_and_slices():
     assert _datums(pr.serialize_record_batch(extra, sj, 1)) == recs
 
 
+def test_large_batch_takes_the_staged_upload_and_round_trips():
+    """Above 4 MiB of Arrow buffers the upload goes through the pinned gather pipeline (encode.cu); the bytes
+    that come back must still be the input datums (decode -> encode identity), for whole and sliced batches."""
+    import numpy as np
+    import workloads
+    n = 200_000
+    sj, data, off = workloads.generate("kafka", n, seed=11)
+    batch = pr.decode_packed(data, off, n, sj, 1)[0]
+    assert batch.nbytes > (16 << 20)
+    for b, lo, k in ((batch, 0, 3), (batch.slice(12_345, 150_000), 12_345, 2)):
+        out = pr.serialize_record_batch(b, sj, k)
+        got = np.concatenate([np.frombuffer(a.buffers()[2], dtype=np.uint8)[:a.offsets[-1].as_py()] for a in out])
+        assert got.tobytes() == data[off[lo]:off[lo + b.num_rows]].tobytes()
+        lens = np.concatenate([np.diff(np.frombuffer(a.buffers()[1], dtype=np.int32)[:len(a) + 1]) for a in out])
+        assert np.array_equal(lens, np.diff(off[lo:lo + b.num_rows + 1]))
+
+
 def test_error_surface():
     recs = [bytes.fromhex(G.G2_HEX)]
     batch = pr.deserialize_array(recs, G.G2_SCHEMA)
