@@ -69,9 +69,10 @@ def test_large_batch_takes_the_staged_upload_and_round_trips():
     assert batch.nbytes > (16 << 20)
     for b, lo, k in ((batch, 0, 3), (batch.slice(12_345, 150_000), 12_345, 2)):
         out = pr.serialize_record_batch(b, sj, k)
-        got = np.concatenate([np.frombuffer(a.buffers()[2], dtype=np.uint8)[:a.offsets[-1].as_py()] for a in out])
+        offs = [np.frombuffer(a.buffers()[1], dtype=np.int32)[:len(a) + 1] for a in out]
+        got = np.concatenate([np.frombuffer(a.buffers()[2], dtype=np.uint8)[:o[-1]] for a, o in zip(out, offs)])
         assert got.tobytes() == data[off[lo]:off[lo + b.num_rows]].tobytes()
-        lens = np.concatenate([np.diff(np.frombuffer(a.buffers()[1], dtype=np.int32)[:len(a) + 1]) for a in out])
+        lens = np.concatenate([np.diff(o) for o in offs])
         assert np.array_equal(lens, np.diff(off[lo:lo + b.num_rows + 1]))
 
 
