@@ -14,6 +14,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -530,6 +533,17 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
     if (!rv_schema_is_supported(s)) { rv_set_last_error("schema is outside the direct-encode subset; this library has no Value-tree CPU fallback"); return RV_ERR_SCHEMA; }
     const AvroNode* top = static_cast<const AvroNode*>(rv_schema_avro_root(s));
     if (std::strcmp(batch_schema->format, "+s") != 0) { rv_set_last_error("fast_encode: expected StructArray"); return RV_ERR_INVALID; }
+    // RV_TRACE=1: phase times of this call on stderr (each mark drains the stream first; development aid)
+    static const bool trace = std::getenv("RV_TRACE") && std::getenv("RV_TRACE")[0] == '1';
+    auto t_prev = std::chrono::steady_clock::now();
+    std::string trace_line;
+    auto mark = [&](const char* what) {
+        if (!trace) return;
+        cudaStreamSynchronize(nullptr);
+        const auto now = std::chrono::steady_clock::now();
+        trace_line += std::string(what) + "=" + std::to_string(std::chrono::duration<double, std::milli>(now - t_prev).count()).substr(0, 6) + "ms ";
+        t_prev = now;
+    };
     EncBuilder b;
     try {
         b.record_children(*top, batch, batch_schema, batch->offset, 1, 0, 0);
@@ -557,8 +571,17 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
     // fraction of PCIe speed (the driver stages every piece itself, serially).  Instead a few host threads gather
     // 16 MiB pieces into one pinned arena (same layout as the device arena) and each piece's H2D copy is issued as
     // soon as it has landed, so the gather of piece i+1 overlaps the DMA of piece i.
+    mark("plan");
     std::shared_ptr<void> h_in_keep;
-    if (total >= (size_t(4) << 20)) {
+    // (buffers that already live in pinned / registered memory — e.g. batches this library decoded — go direct)
+    bool pageable = false;
+    for (size_t i = 0; i < b.bufs.size() && !pageable; ++i) {
+        if (b.bufs[i].bytes < (size_t(1) << 20)) continue;
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, b.bufs[i].ptr) != cudaSuccess) { (void)cudaGetLastError(); pageable = true; }
+        else pageable = at.type == cudaMemoryTypeUnregistered;
+    }
+    if (pageable && total >= (size_t(4) << 20)) {
         uint8_t* h_in = static_cast<uint8_t*>(rv_host_alloc(total));
         if (!h_in) return RV_ERR_CUDA;
         h_in_keep = std::shared_ptr<void>(h_in, [](void* q) { rv_host_free(q); });
@@ -605,6 +628,7 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
     if (!b.sym_off.empty()) ENC_CUDA(cudaMemcpyAsync(d_symoff.p, b.sym_off.data(), b.sym_off.size() * 4, cudaMemcpyHostToDevice, nullptr));
     if (!b.sym_bytes.empty()) ENC_CUDA(cudaMemcpyAsync(d_symbytes.p, b.sym_bytes.data(), b.sym_bytes.size(), cudaMemcpyHostToDevice, nullptr));
 
+    mark("upload");
     EncParams p{};
     p.nodes = static_cast<const ENode*>(d_nodes.p); p.n_nodes = int32_t(b.nodes.size());
     p.sym_off = static_cast<const int32_t*>(d_symoff.p); p.sym_bytes = static_cast<const uint8_t*>(d_symbytes.p);
@@ -636,6 +660,7 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
         ENC_CUDA(cudaMemcpyAsync(&err_word, d_err.p, 8, cudaMemcpyDeviceToHost, nullptr));
         ENC_CUDA(cudaMemcpyAsync(chunk_tot.data(), d_tot.p, size_t(k) * 8, cudaMemcpyDeviceToHost, nullptr));
         ENC_CUDA(cudaStreamSynchronize(nullptr));
+        mark("size+scan");
         if (err_word != ~0ull) {
             const uint32_t code = uint32_t(err_word & 0xFF);
             const std::string what = code == EE_ENUM ? "fast_encode: enum symbol not in schema"
@@ -675,8 +700,10 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
             attr_set = true;
         }
         p.stage_cap = uint32_t(stage);
+        mark("alloc_out");
         encode_write_kernel<<<unsigned(n_tiles), kBlock, stage>>>(p);
         ENC_CUDA(cudaGetLastError());
+        mark("write");
     }
     for (int j = 0; j < k; ++j) {
         auto& c = res->chunks[size_t(j)];
@@ -688,6 +715,8 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
         ENC_CUDA(cudaMemcpyAsync(h, d_out[size_t(j)].p, bytes, cudaMemcpyDeviceToHost, nullptr));
     }
     ENC_CUDA(cudaStreamSynchronize(nullptr));
+    mark("download");
+    if (trace) std::fprintf(stderr, "[rv trace encode] %s\n", trace_line.c_str());
     *out = res.release();
     return RV_OK;
 }
