@@ -173,3 +173,36 @@ def test_arrow_array_ingest_view_is_zero_copy_and_rebased():
         pr._packed_view(pa.array([1, 2]))
     with pytest.raises(OverflowError):
         pr.deserialize_arrow_array(pa.array(recs, type=pa.binary()), "{}", -1)
+
+
+def test_specialised_kernels_compile_for_sm100a_and_use_the_copy_engine(tmp_path, monkeypatch):
+    """No GPU needed: NVRTC cross-compiles the schema-specialised kernels for sm_100a.  The cubin must hold both
+    kernels and the Blackwell bulk-copy path: TMA load of the input window (UBLKCP.S.G + mbarrier SYNCS) in both,
+    TMA store of the staged strings (UBLKCP.G.S) in emit."""
+    import glob
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    monkeypatch.setenv("RV_JIT_CACHE", str(tmp_path))
+    s = pr.Schema(G.G345_SCHEMA)
+    s.precompile("sm_100a")
+    assert "op_str<MODE" in s.walker_source and "struct Walker" in s.walker_source
+    cubins = glob.glob(str(tmp_path / "*.cubin"))
+    assert len(cubins) == 1
+    sass = subprocess.run([cuobjdump, "-sass", cubins[0]], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in sass or "SM100" in sass.upper() or "EF_CUDA_SM100" in sass
+    fn = {}
+    cur = None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split(":")[1].strip()
+            fn[cur] = []
+        elif cur:
+            fn[cur].append(line)
+    assert set(fn) == {"rvj_count", "rvj_emit"}
+    count, emit = "\n".join(fn["rvj_count"]), "\n".join(fn["rvj_emit"])
+    for body in (count, emit):
+        assert "UBLKCP.S.G" in body and "SYNCS.ARRIVE.TRANS64" in body and "TRYWAIT" in body
+    assert "UBLKCP.G.S" in emit and "UBLKCP.G.S" not in count
