@@ -393,6 +393,7 @@ const char* err_text(uint32_t code) {
 struct HostScratch {
     uint8_t* p = nullptr;
     size_t cap = 0;
+    ~HostScratch() { if (p) { cudaFreeHost(p); (void)cudaGetLastError(); } }  // worker threads of the chunk pipeline end with the call
     uint8_t* get(size_t bytes) {
         if (bytes > cap) {
             if (p) cudaFreeHost(p);
@@ -410,6 +411,7 @@ thread_local HostScratch t_scratch;
 struct EventPool {  // cudaEventCreate/Destroy per call is measurable at small batch sizes
     cudaEvent_t ev[8] = {};
     int device = -1;
+    ~EventPool() { for (auto& e : ev) if (e) cudaEventDestroy(e); (void)cudaGetLastError(); }
     cudaError_t get(int dev, cudaEvent_t** out) {
         if (device != dev) {
             for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
@@ -937,6 +939,7 @@ rv_status rv_decode_host(const rv_schema* s_, const uint8_t* data, const int64_t
     std::mutex acc_mu;
     float acc[6] = {0, 0, 0, 0, 0, 0};
     int acc_launches = 0;
+    long long acc_overflow = 0;
     const char* walker = "none";
     auto worker = [&](int wid) {
         cudaSetDevice(device);
@@ -953,6 +956,7 @@ rv_status rv_decode_host(const rv_schema* s_, const uint8_t* data, const int64_t
             acc[4] += hm;
             acc[5] += dm;
             acc_launches += t_launches;
+            acc_overflow += t_overflow_tiles;
             walker = t_walker;
         }
     };
@@ -964,6 +968,7 @@ rv_status rv_decode_host(const rv_schema* s_, const uint8_t* data, const int64_t
     for (auto& t : threads) t.join();
     for (int q = 0; q < 6; ++q) t_timings[q] = acc[q];
     t_launches = acc_launches;
+    t_overflow_tiles = acc_overflow;
     t_walker = walker;
     auto res = std::make_unique<rv_result>();
     res->schema = rv_schema_retain(s);
