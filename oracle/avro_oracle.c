@@ -232,7 +232,15 @@ static asch *aparse(const jval *j, int *err) {
         if (!fs || fs->k != J_ARR) { *err = 1; return NULL; }
         asch *r = anew(A_RECORD);
         r->n = fs->n; r->sub = xmalloc(sizeof(asch *) * (size_t)(fs->n ? fs->n : 1));
-        for (int i = 0; i < fs->n; i++) r->sub[i] = aparse(jget(fs->items[i], "type"), err);
+        for (int i = 0; i < fs->n; i++) {
+            /* apache-avro 0.21 RecordField::parse -> Parser::parse_complex(field): with a bare-string "type" the
+               type's attributes (items / values / symbols / logicalType) are read from the FIELD object
+               (ruhvro/src/serialize.rs:185 relies on it); a bare "record" is a named look-up -> unsupported Ref */
+            const jval *f = fs->items[i];
+            const jval *ft = f && f->k == J_OBJ ? jget(f, "type") : NULL;
+            if (ft && ft->k == J_STR && strcmp(ft->s, "record") && strcmp(ft->s, "error")) r->sub[i] = aparse(f, err);
+            else r->sub[i] = aparse(ft, err);
+        }
         return r;
     }
     if (!strcmp(t->s, "enum")) {

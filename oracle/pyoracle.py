@@ -102,7 +102,12 @@ def _parse(j: Any, ns: Optional[str]) -> AvroSchema:
         return _parse(t, ns)
     if t in ("record", "error"):
         full, rns = _name(j, ns)
-        fields = [(f["name"], _parse(f["type"], rns), f.get("doc")) for f in j["fields"]]
+        # apache-avro 0.21 RecordField::parse hands the FIELD object to Parser::parse_complex: with a bare-string
+        # "type", items / values / symbols / logicalType are read from the field object (ruhvro/src/serialize.rs:185
+        # relies on {"name":..,"type":"array","items":..}); a bare "record" is a named look-up -> unsupported Ref
+        fields = [(f["name"],
+                   _parse(f if isinstance(f["type"], str) and f["type"] not in ("record", "error") else f["type"], rns),
+                   f.get("doc")) for f in j["fields"]]
         return AvroSchema("record", fullname=full, doc=j.get("doc"), aliases=_fix_aliases(j.get("aliases"), rns), fields=fields)
     if t == "enum":
         full, ens = _name(j, ns)

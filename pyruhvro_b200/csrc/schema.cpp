@@ -128,7 +128,14 @@ std::unique_ptr<AvroNode> parse_node(const Json& j, const std::string& ns, int d
             const Json* ft = fj.find("type");
             if (!fn || !fn->is_string() || !ft) bad("record field needs \"name\" and \"type\"");
             f.name = fn->str;
-            f.type = parse_node(*ft, rns, depth + 1);
+            // apache-avro 0.21 parses a record field by handing the FIELD object to its complex-type parser
+            // (RecordField::parse -> Parser::parse_complex(field, ..)), so when "type" is a bare string the
+            // attributes of that type are read from the field object itself: {"name":"xs","type":"array","items":..}
+            // is an array (the reference relies on it: ruhvro/src/serialize.rs:185-186), an "enum" takes the field's
+            // name and "symbols", and a field-level "logicalType" annotates a primitive.  A bare "record" there is a
+            // look-up of an already defined type by the field's name: a named reference, which the gate rejects.
+            if (ft->is_string() && ft->str != "record" && ft->str != "error") f.type = parse_node(fj, rns, depth + 1);
+            else f.type = parse_node(*ft, rns, depth + 1);
             if (const Json* d = fj.find("doc"); d && d->is_string()) { f.has_doc = true; f.doc = d->str; }
             r->fields.push_back(std::move(f));
         }

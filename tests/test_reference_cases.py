@@ -153,3 +153,105 @@ def test_gpu_encodes_the_reference_case(name):
     out = [bytes(x.as_py()) for x in chunks[0]]
     assert out == recs
     assert pr.deserialize_array(out, sj).equals(batch)
+
+
+# ---- ruhvro/src/schema_translate.rs:304-341 -------------------------------------------------------------------
+def test_field_names_use_avro_field_name():
+    import pyruhvro_b200 as pr
+    sj = """{"type": "record", "name": "User", "namespace": "com.example", "fields": [
+        {"name": "userid", "type": "string"},
+        {"name": "address", "type": ["null", {"type": "record", "name": "Address", "fields": [
+            {"name": "street", "type": "string"}, {"name": "city", "type": "string"}]}], "default": null},
+        {"name": "class", "type": {"type": "enum", "name": "ClassEnum", "symbols": ["A", "B", "C"]}}]}"""
+    for schema in (po.to_arrow_schema(po.parse_schema(sj)), pr.Schema(sj).arrow_schema):
+        assert schema.names == ["userid", "address", "class"]
+        address = schema.field("address").type
+        assert pa.types.is_struct(address) and [address.field(i).name for i in range(address.num_fields)] == ["street", "city"]
+
+
+# ---- ruhvro/src/serialize.rs:114-207, 263-310, 361-422 (Arrow built by hand -> serialize -> deserialize) ---------
+CONVERT_SCHEMA = """{"type": "record", "name": "test", "fields": [
+    {"name": "int_arr_1", "type": "int"},
+    {"name": "int_arr_2", "type": ["null","int"]},
+    {"name": "str_arr_1", "type": "string"},
+    {"name": "str_arr_2", "type": ["null", "string"]},
+    {"name": "list_arr", "type": "array", "items": ["null", "int"]},
+    {"name": "list_arr2", "type": ["null", {"type": "array", "items": ["null", "int"]}]},
+    {"name": "timestamp_arr", "type": {"type": "long", "logicalType": "timestamp-millis"}}]}"""
+MAP_SCHEMA = """{"type": "record", "name": "test", "fields": [{"name": "map_field", "type": {"type": "map", "values": "int"}}]}"""
+AB_SCHEMA = """{"type": "record", "name": "test", "fields": [{"name": "a", "type": "int"}, {"name": "b", "type": "string"}]}"""
+
+
+def _convert_batch():
+    """test_convert_to_avro's StructArray (serialize.rs:116-170).  Note the schema's field-level
+    {"type": "array", "items": ...} shorthand (:185): apache-avro reads a field's type attributes from the field."""
+    item = pa.field("item", pa.int32(), True)
+    return pa.RecordBatch.from_arrays([
+        pa.array([1, 2, 3, 4], pa.int32()),
+        pa.array([1, None, None, 2], pa.int32()),
+        pa.array(["one", "two", "three", "four"]),
+        pa.array(["one", None, "three", None]),
+        pa.array([[1, 2, 3], [2, 3], [], [None, 2, 3]], pa.list_(item)),
+        pa.array([[1, 2, 3], None, [], [None, 2, 3]], pa.list_(item)),
+        pa.array([1, 2, 3, 4], pa.timestamp("ms")),
+    ], schema=pa.schema([
+        pa.field("int_arr_1", pa.int32(), False), pa.field("int_arr_2", pa.int32(), True),
+        pa.field("str_arr_1", pa.string(), False), pa.field("str_arr_2", pa.string(), True),
+        pa.field("list_arr", pa.list_(item), False), pa.field("list_arr2", pa.list_(item), True),
+        pa.field("timestamp_arr", pa.timestamp("ms"), False)]))
+
+
+def _map_batch():
+    """test_map_record_round_trip's MapArray::new_from_strings(["a","b"], [13, 2], offsets [0,1,2]) (serialize.rs:279-296)."""
+    typ = pa.map_(pa.string(), pa.field("values", pa.int32(), False))
+    return pa.RecordBatch.from_arrays([pa.array([[("a", 13)], [("b", 2)]], typ)],
+                                      schema=pa.schema([pa.field("map_field", typ, False)]))
+
+
+def _same_rows(a: pa.RecordBatch, b: pa.RecordBatch):
+    assert a.num_rows == b.num_rows and a.schema.names == b.schema.names
+    assert _rows(a) == _rows(b)
+
+
+def test_convert_to_avro_and_map_round_trip_through_the_oracles(coracle):
+    """serialize (fast_encode.rs restatement) -> deserialize (fast_decode.rs restatement) returns the batch."""
+    for sj, batch in ((CONVERT_SCHEMA, _convert_batch()), (MAP_SCHEMA, _map_batch())):
+        s = po.parse_schema(sj)
+        assert po.is_supported(s)
+        chunks = po.py_encode(s, batch, 1)
+        assert len(chunks) == 1 and len(chunks[0]) == batch.num_rows
+        back = po.canon_to_batch(coracle.decode(sj, chunks[0]), po.to_arrow_schema(s))
+        _same_rows(back, batch)
+        assert po.canon_diff(coracle.decode(sj, chunks[0]), po.py_decode(s, chunks[0])) is None
+
+
+def test_serialize_matches_columns_by_name_and_errors_on_missing_column_oracle():
+    s = po.parse_schema(AB_SCHEMA)
+    a, b = pa.array([1, 2, 3], pa.int32()), pa.array(["x", "y", "z"])
+    in_order = pa.RecordBatch.from_arrays([a, b], names=["a", "b"])
+    reversed_ = pa.RecordBatch.from_arrays([b, a], names=["b", "a"])
+    assert po.py_encode(s, in_order, 1) == po.py_encode(s, reversed_, 1)
+    with pytest.raises(po.EncodeError, match="missing column 'b'"):
+        po.py_encode(s, pa.RecordBatch.from_arrays([a], names=["a"]), 1)
+
+
+@pytest.mark.gpu
+def test_gpu_convert_to_avro_and_map_round_trip(coracle):
+    import pyruhvro_b200 as pr
+    for sj, batch in ((CONVERT_SCHEMA, _convert_batch()), (MAP_SCHEMA, _map_batch())):
+        chunks = pr.serialize_record_batch(batch, sj, 1)
+        assert len(chunks) == 1 and len(chunks[0]) == batch.num_rows
+        datums = [bytes(x.as_py()) for x in chunks[0]]
+        assert [datums] == po.py_encode(po.parse_schema(sj), batch, 1)      # same bytes as the fast_encode.rs restatement
+        _same_rows(pr.deserialize_array(datums, sj), batch)                 # and the reference's assertion
+
+
+@pytest.mark.gpu
+def test_gpu_serialize_matches_columns_by_name_and_errors_on_missing_column():
+    import pyruhvro_b200 as pr
+    a, b = pa.array([1, 2, 3], pa.int32()), pa.array(["x", "y", "z"])
+    in_order = pr.serialize_record_batch(pa.RecordBatch.from_arrays([a, b], names=["a", "b"]), AB_SCHEMA, 1)
+    reversed_ = pr.serialize_record_batch(pa.RecordBatch.from_arrays([b, a], names=["b", "a"]), AB_SCHEMA, 1)
+    assert len(in_order) == len(reversed_) == 1 and in_order[0].equals(reversed_[0])
+    with pytest.raises(ValueError, match="missing column 'b'"):
+        pr.serialize_record_batch(pa.RecordBatch.from_arrays([a], names=["a"]), AB_SCHEMA, 1)
