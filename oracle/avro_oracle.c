@@ -692,10 +692,19 @@ static int has_null_child(const dec *d) {
     for (int i = 0; i < d->nchild; i++) { if (!d->child[i] || has_null_child(d->child[i])) return 1; }
     return 0;
 }
+/* A record with no fields always fails at finish: nested -> "RecordDecoder produced a record with 0 fields"
+   (fast_decode.rs:633-635); top level -> RecordBatch::try_new with no columns (:834). */
+static int has_empty_record(const asch *a) {
+    if (!a) return 0;
+    if (a->k == A_RECORD && a->n == 0) return 1;
+    if (a->k == A_RECORD || a->k == A_UNION || a->k == A_ARRAY || a->k == A_MAP)
+        for (int i = 0; i < a->n; i++) if (has_empty_record(a->sub[i])) return 1;
+    return 0;
+}
 /* decode_with_arrow_schema (fast_decode.rs:815-835) over rows [r0, r1) of the packed input */
 static orc_batch *decode_range(const orc_schema *s, const uint8_t *data, const int64_t *offsets, int64_t r0, int64_t r1) {
     orc_batch *b = xmalloc(sizeof *b); memset(b, 0, sizeof *b); b->err_record = -1;
-    if (!orc_schema_is_supported(s)) { b->err = E_SCHEMA; return b; }
+    if (!orc_schema_is_supported(s) || has_empty_record(s->schema)) { b->err = E_SCHEMA; return b; }
     g_cap = (size_t)(r1 - r0);
     dec *top = make_record_decoder(s->schema, 0);
     if (has_null_child(top)) { dfree(top); b->err = E_SCHEMA; return b; } /* "unsupported nullable inner type" :338 */

@@ -562,9 +562,23 @@ def _finish(d: _Dec) -> dict:
     return _canon("map", n, nc, v, [d.offsets], [entries])
 
 
+def _has_empty_record(s: AvroSchema) -> bool:
+    """A record with no fields always fails at finish: nested -> "RecordDecoder produced a record with 0 fields"
+    (fast_decode.rs:633-635); top level -> RecordBatch::try_new with no columns (:834)."""
+    if s.kind == "record":
+        return not s.fields or any(_has_empty_record(f[1]) for f in s.fields)
+    if s.kind == "union":
+        return any(_has_empty_record(v) for v in s.variants)
+    if s.kind == "array":
+        return _has_empty_record(s.items)
+    if s.kind == "map":
+        return _has_empty_record(s.values)
+    return False
+
+
 def py_decode(schema: AvroSchema, records: List[bytes]) -> List[dict]:
     """decode_with_arrow_schema (fast_decode.rs:815-835): canonical columns of one batch."""
-    if not is_supported(schema):
+    if not is_supported(schema) or _has_empty_record(schema):
         raise DecodeError("schema")
     top = [_make(f[1]) for f in schema.fields]
     for r, rec in enumerate(records):

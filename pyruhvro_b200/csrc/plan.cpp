@@ -232,6 +232,8 @@ struct Builder {
 Plan build_plan(const AvroNode& top, const std::vector<ArrowField>& fields) {
     if (top.k != AK::Record) throw std::runtime_error("fast_decode::decode called on non-record schema");  // :820-823
     if (top.fields.size() != fields.size()) throw std::runtime_error("avro/arrow field count mismatch");
+    // RecordBatch::try_new(schema, vec![]) at fast_decode.rs:834 (arrow-rs: a batch needs a column or a row count)
+    if (top.fields.empty()) throw std::runtime_error("must either specify a row count or at least one column");
     Builder b;
     b.p.space_stream.push_back(-1);
     b.p.space_depth.push_back(0);

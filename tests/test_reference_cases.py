@@ -255,3 +255,53 @@ def test_gpu_serialize_matches_columns_by_name_and_errors_on_missing_column():
     assert len(in_order) == len(reversed_) == 1 and in_order[0].equals(reversed_[0])
     with pytest.raises(ValueError, match="missing column 'b'"):
         pr.serialize_record_batch(pa.RecordBatch.from_arrays([a], names=["a"]), AB_SCHEMA, 1)
+
+
+# ---- SURVEY.md A.3 edge cases that need no GPU -------------------------------------------------------------------
+def test_records_without_fields_fail_like_the_reference(coracle):
+    """Nested: "RecordDecoder produced a record with 0 fields" (fast_decode.rs:633-635); top level:
+    RecordBatch::try_new with no columns (:834).  The reference's gate (:38-61) still says "supported" — the failure is
+    at finish; rv_schema_is_supported answers "can this library decode it" and may say 0 (nothing can decode it)."""
+    import numpy as np
+    import pyruhvro_b200 as pr
+    top = '{"type":"record","name":"E","fields":[]}'
+    nested = ('{"type":"record","name":"O","fields":[{"name":"a","type":"int"},'
+              '{"name":"e","type":["null",{"type":"record","name":"E","fields":[]}]}]}')
+    for sj, text in ((top, "at least one column"), (nested, "record with 0 fields")):
+        s = po.parse_schema(sj)
+        assert po.is_supported(s)
+        with pytest.raises(po.DecodeError):
+            po.py_decode(s, [b"\x02\x00"])
+        with pytest.raises(po.DecodeError):
+            coracle.decode(sj, [b"\x02\x00"])
+        with pytest.raises(ValueError, match=text):   # raised from the plan, before any CUDA call
+            pr.decode_packed(np.frombuffer(b"\x02\x00", dtype=np.uint8), np.array([0, 2]), 1, sj, 1)
+
+
+def test_two_variant_union_without_null_is_a_sparse_union(coracle):
+    """["string","int"]: no null branch, so it is NOT folded into a nullable column — a non-nullable sparse union of two
+    (fast_decode.rs:376-384, schema_translate.rs:78-104)."""
+    import pyruhvro_b200 as pr
+    sj = '{"type":"record","name":"U","fields":[{"name":"u","type":["string","int"]}]}'
+    s = po.parse_schema(sj)
+    for schema in (po.to_arrow_schema(s), pr.Schema(sj).arrow_schema):
+        f = schema.field("u")
+        assert pa.types.is_union(f.type) and f.type.mode == "sparse" and f.type.num_fields == 2 and not f.nullable
+        assert [f.type.field(i).name for i in range(2)] == ["varchar", "int"]
+    recs = [po.encode_datum(s, {"u": (0, "abc")}), po.encode_datum(s, {"u": (1, -7)}), po.encode_datum(s, {"u": (0, "")})]
+    c = coracle.decode(sj, recs)
+    assert po.canon_diff(c, po.py_decode(s, recs)) is None
+    batch = po.canon_to_batch(c, po.to_arrow_schema(s))
+    assert batch.column("u").to_pylist() == ["abc", -7, ""]
+    assert batch.column("u").type_codes.to_pylist() == [0, 1, 0]
+    with pytest.raises(po.DecodeError):                    # branch index 2 is out of range (:643-658)
+        coracle.decode(sj, [b"\x04"])
+
+
+def test_chunk_partition_rule():
+    """deserialize.rs:53-68: k = clamp(num_chunks, 1, max(n, 1)); equal floors, the last chunk takes the remainder."""
+    import pyruhvro_b200 as pr
+    assert [b - a for a, b in po.chunk_bounds(10, po.clamp_chunks(4, 10))] == [2, 2, 2, 4]
+    assert po.clamp_chunks(0, 10) == 1 and po.clamp_chunks(99, 3) == 3 and po.clamp_chunks(5, 0) == 1
+    shards = pr.distributed.shard_bounds if hasattr(pr, "distributed") else None
+    assert shards is None or callable(shards)
