@@ -124,6 +124,9 @@ def test_oracles_reproduce_the_reference_case(name, coracle):
     assert _rows(c_batch) == want
     assert _rows(py_batch) == want
     assert po.canon_diff(coracle.decode(sj, recs), po.py_decode(s, recs)) is None
+    if name == "decodes_multi_variant_union":   # the null variant keeps its real type_id (fast_decode.rs:649-656)
+        assert c_batch.column("u").type_codes.to_pylist() == [0, 1, 2, 3] * 2
+        assert pa.types.is_null(c_batch.column("u").type.field(0).type)
 
 
 @pytest.mark.gpu
