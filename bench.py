@@ -340,7 +340,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": total_in + idx_bytes, "d2h_bytes_per_step": buffer_bytes,
                 "ms_per_step": 1000.0 * e2e_s / steps, "h2d_ms": h2d_ms / steps, "d2h_ms": d2h_ms / steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "emit_kernel", "achieved": emit_gbs, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "rvj_emit" if pr.last_walker() == "jit" else "emit_kernel", "achieved": emit_gbs, "peak": peak, "unit": "GB/s",
                      "frac": emit_gbs / peak, "traffic": traffic, "algorithmic_bytes": emit_bytes, "kernel_ms": kt[2],
                      "peak_source": peak_src,
                      "count_kernel": {"achieved": count_gbs, "frac": count_gbs / peak, "algorithmic_bytes": count_bytes, "kernel_ms": kt[0]},
