@@ -1,16 +1,17 @@
 // Kernel bodies of the decode, templated over the walker (InterpWalker or a generated,
 // schema-specialised walker).  Device-only; compiled by nvcc (kernels.cu) and by NVRTC (jit.cpp).
 //
-//   count_body  one CTA per 256-record tile: stage the tile's contiguous byte window in shared
-//               memory (coalesced 128-bit loads), COUNT-walk every record (full validation),
-//               CTA-reduce per-stream totals -> tile_agg.
-//   emit_body   same staging; COUNT walk -> CTA-wide exclusive scan of the lane counts (+ the tile's
-//               base from scan_kernel) -> EMIT walk.  Utf8 bytes are assembled per column in a
-//               shared-memory staging area and written out with coalesced 128-bit stores; fixed-width
-//               values / offsets are stored row-aligned; space-0 validity is one ballot word per warp.
+//   count_body  one CTA per 256-record tile: one TMA bulk copy (cp.async.bulk + mbarrier) stages the tile's
+//               contiguous byte window in shared memory, every lane COUNT-walks its record (full validation),
+//               a warp-per-stream scan turns the lane counts into in-tile prefixes -> lane_off, tile_agg.
+//   emit_body   same staging; the lanes' cursors (tile base from scan_kernel + in-tile prefix from count) are
+//               loaded while the window is in flight -> EMIT walk.  Utf8 bytes are assembled per column in a
+//               shared-memory staging area and leave through TMA bulk stores (16-byte aligned body) plus a few
+//               head/tail bytes; fixed-width values / offsets are stored row-aligned; space-0 validity is one
+//               ballot word per warp.
 //
-// Shared-memory map (dynamic, rv_smem):
-//   [nodes n_nodes*32][wtot S*8*4 (emit: tile bases)][tot (S+1)*4][adj S*4][ptrs n_slots*8][cur S*256*4][in: smem_data_cap][out: smem_stage_cap]
+// Shared-memory map (dynamic, rv_smem; smem_map() in dev_types.h):
+//   [nodes n_nodes*32][wtot S*8*4 (emit: tile bases)][tot (S+1)*4][adj S*4][mbar 8][ptrs n_slots*8][cur S*256*4][in: smem_data_cap][out: smem_stage_cap]
 //   (register-cursor walkers: `cur` overlays `in`)
 #pragma once
 #include "dev_core.cuh"
