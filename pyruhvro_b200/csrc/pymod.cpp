@@ -2,8 +2,8 @@
 // be native — walking a Python list[bytes] and releasing the GIL around the decode.
 //
 // Mirrors src/lib.rs of the reference:
-//   extract_bytes_list  (:29-33)  elements must be `bytes`; references are held for the call
-//   py.detach(...)      (:64-69,82-87)  the GIL is released around packing + decode
+//   extract_bytes_list  (:29-33)  elements must be `bytes`
+//   py.detach(...)      (:64-69,82-87)  the GIL is released around the decode (packing keeps it: see pack_list)
 //   to_py_err           (:25-27)  failures surface as ValueError(str)
 // Packing into one contiguous buffer + offsets is what the reference itself does with
 // BinaryArray::from_vec (ruhvro/src/deserialize.rs:90); here it lands in pinned host memory so
@@ -13,7 +13,9 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -21,10 +23,76 @@
 
 namespace {
 
-struct Pinned {
-    void* p = nullptr;
-    explicit Pinned(size_t n) : p(rv_host_alloc(n)) {}
-    ~Pinned() { rv_host_free(p); }
+// Packs a list[bytes] into one contiguous buffer + i64 offsets (what BinaryArray::from_vec builds at
+// ruhvro/src/deserialize.rs:90).  The GIL is HELD for the whole function: the elements are only borrowed, and
+// nothing can mutate the list or free an element while no other Python thread can run — so the walk is one
+// read of each object header (type, size, payload pointer) with no INCREF/DECREF passes, which were two thirds of
+// its cost.  The payload gather fans out over plain C++ threads (they touch no Python state).
+// `alloc(bytes)` returns the destination memory (pinned for the decode path).  Returns false with a Python
+// exception set.
+struct Packed {
+    char* data = nullptr;
+    int64_t* offsets = nullptr;
+    int64_t total = 0;
+    Py_ssize_t n = 0;
+};
+
+template <class Alloc>
+bool pack_list(PyObject* list, Alloc alloc, Packed* out) {
+    const Py_ssize_t n = PyList_GET_SIZE(list);
+    out->n = n;
+    out->offsets = static_cast<int64_t*>(alloc((static_cast<size_t>(n) + 1) * 8));
+    if (!out->offsets) {
+        PyErr_SetString(PyExc_ValueError, "pinned host allocation failed (is a CUDA device present?)");
+        return false;
+    }
+    std::unique_ptr<const char*[]> ptrs(new const char*[static_cast<size_t>(n) + 1]);  // uninitialised on purpose
+    int64_t* offsets = out->offsets;
+    offsets[0] = 0;
+    for (Py_ssize_t i = 0; i < n; ++i) {
+        PyObject* item = PyList_GET_ITEM(list, i);
+        if (!PyBytes_Check(item)) {
+            PyErr_Format(PyExc_TypeError, "argument 'list': element %zd is '%s', expected 'bytes'", i, Py_TYPE(item)->tp_name);
+            return false;
+        }
+        ptrs[static_cast<size_t>(i)] = PyBytes_AS_STRING(item);
+        offsets[i + 1] = offsets[i] + static_cast<int64_t>(PyBytes_GET_SIZE(item));
+    }
+    const int64_t total = offsets[n];
+    out->total = total;
+    out->data = static_cast<char*>(alloc(static_cast<size_t>(total) + 64));
+    if (!out->data) {
+        PyErr_SetString(PyExc_ValueError, "pinned host allocation failed (is a CUDA device present?)");
+        return false;
+    }
+    const unsigned workers = total > (int64_t(8) << 20) ? std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+    char* dst = out->data;
+    const char* const* src = ptrs.get();
+    auto copy_range = [dst, src, offsets](Py_ssize_t a, Py_ssize_t b) {
+        for (Py_ssize_t i = a; i < b; ++i) std::memcpy(dst + offsets[i], src[i], static_cast<size_t>(offsets[i + 1] - offsets[i]));
+    };
+    if (workers <= 1) {
+        copy_range(0, n);
+    } else {
+        // split by BYTES, not by element count, so skewed inputs still balance
+        std::vector<std::thread> th;
+        Py_ssize_t a = 0;
+        for (unsigned w = 0; w < workers; ++w) {
+            const int64_t want = total / int64_t(workers) * int64_t(w + 1);
+            const Py_ssize_t b = (w + 1 == workers) ? n : Py_ssize_t(std::upper_bound(offsets, offsets + n + 1, want) - offsets - 1);
+            const Py_ssize_t bb = std::max(a, std::min(b, n));
+            th.emplace_back(copy_range, a, bb);
+            a = bb;
+        }
+        for (auto& t : th) t.join();
+    }
+    return true;
+}
+
+struct PinnedPair {  // the two slabs of one call
+    void* a = nullptr;
+    void* b = nullptr;
+    ~PinnedPair() { rv_host_free(a); rv_host_free(b); }
 };
 
 // decode_list(schema_handle: int, records: list[bytes], num_chunks: int) -> result handle (int)
@@ -34,62 +102,21 @@ PyObject* decode_list(PyObject*, PyObject* args) {
     long long num_chunks = 1;
     if (!PyArg_ParseTuple(args, "KO!L", &schema_addr, &PyList_Type, &list, &num_chunks)) return nullptr;
     const rv_schema* schema = reinterpret_cast<const rv_schema*>(static_cast<uintptr_t>(schema_addr));
-    const Py_ssize_t n = PyList_GET_SIZE(list);
-
-    // Pass 1 (GIL held): type-check, take references, record pointers and sizes.
-    std::vector<PyObject*> held(static_cast<size_t>(n));
-    std::vector<const char*> ptrs(static_cast<size_t>(n));
-    std::vector<int64_t> offsets(static_cast<size_t>(n) + 1);
-    offsets[0] = 0;
-    for (Py_ssize_t i = 0; i < n; ++i) {
-        PyObject* item = PyList_GET_ITEM(list, i);
-        if (!PyBytes_Check(item)) {
-            for (Py_ssize_t j = 0; j < i; ++j) Py_DECREF(held[static_cast<size_t>(j)]);
-            PyErr_Format(PyExc_TypeError, "argument 'list': element %zd is '%s', expected 'bytes'", i, Py_TYPE(item)->tp_name);
-            return nullptr;
-        }
-        Py_INCREF(item);
-        held[static_cast<size_t>(i)] = item;
-        ptrs[static_cast<size_t>(i)] = PyBytes_AS_STRING(item);
-        offsets[static_cast<size_t>(i) + 1] = offsets[static_cast<size_t>(i)] + static_cast<int64_t>(PyBytes_GET_SIZE(item));
-    }
-    const int64_t total = offsets[static_cast<size_t>(n)];
-
+    PinnedPair slabs;
+    Packed pk;
+    bool first = true;
+    auto alloc = [&](size_t bytes) -> void* {
+        void* p = rv_host_alloc(bytes);
+        (first ? slabs.a : slabs.b) = p;
+        first = false;
+        return p;
+    };
+    if (!pack_list(list, alloc, &pk)) return nullptr;
     rv_result* result = nullptr;
     rv_status st = RV_OK;
-    bool oom = false;
-    Py_BEGIN_ALLOW_THREADS;
-    {
-        Pinned data(static_cast<size_t>(total) + 64), offs((static_cast<size_t>(n) + 1) * 8);
-        if (!data.p || !offs.p) {
-            oom = true;
-        } else {
-            std::memcpy(offs.p, offsets.data(), (static_cast<size_t>(n) + 1) * 8);
-            // Pass 2 (GIL released): gather the payloads, in parallel for large inputs.
-            unsigned workers = total > (int64_t(8) << 20) ? std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
-            auto copy_range = [&](Py_ssize_t a, Py_ssize_t b) {
-                char* dst = static_cast<char*>(data.p);
-                for (Py_ssize_t i = a; i < b; ++i)
-                    std::memcpy(dst + offsets[static_cast<size_t>(i)], ptrs[static_cast<size_t>(i)],
-                                static_cast<size_t>(offsets[static_cast<size_t>(i) + 1] - offsets[static_cast<size_t>(i)]));
-            };
-            if (workers <= 1) {
-                copy_range(0, n);
-            } else {
-                std::vector<std::thread> th;
-                for (unsigned w = 0; w < workers; ++w)
-                    th.emplace_back(copy_range, n * Py_ssize_t(w) / Py_ssize_t(workers), n * Py_ssize_t(w + 1) / Py_ssize_t(workers));
-                for (auto& t : th) t.join();
-            }
-            st = rv_decode_host(schema, static_cast<const uint8_t*>(data.p), static_cast<const int64_t*>(offs.p), n, num_chunks, &result);
-        }
-    }
+    Py_BEGIN_ALLOW_THREADS;  // py.detach (src/lib.rs:64-69,82-87): the decode runs without the GIL
+    st = rv_decode_host(schema, reinterpret_cast<const uint8_t*>(pk.data), pk.offsets, pk.n, num_chunks, &result);
     Py_END_ALLOW_THREADS;
-    for (PyObject* o : held) Py_DECREF(o);
-    if (oom) {
-        PyErr_SetString(PyExc_ValueError, "pinned host allocation failed (is a CUDA device present?)");
-        return nullptr;
-    }
     if (st != RV_OK) {
         PyErr_SetString(PyExc_ValueError, rv_last_error());
         return nullptr;
@@ -97,8 +124,25 @@ PyObject* decode_list(PyObject*, PyObject* args) {
     return PyLong_FromUnsignedLongLong(static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(result)));
 }
 
+// pack(records: list[bytes]) -> (data: bytes, offsets: bytes of int64[n+1]).  The packing step alone, into ordinary
+// memory: lets the CPU test-suite check the list walk / gather without a GPU.
+PyObject* pack(PyObject*, PyObject* args) {
+    PyObject* list = nullptr;
+    if (!PyArg_ParseTuple(args, "O!", &PyList_Type, &list)) return nullptr;
+    std::vector<void*> blocks;
+    auto alloc = [&](size_t bytes) -> void* { void* p = std::malloc(bytes ? bytes : 1); blocks.push_back(p); return p; };
+    Packed pk;
+    PyObject* out = nullptr;
+    if (pack_list(list, alloc, &pk))
+        out = Py_BuildValue("(y#y#)", pk.data, static_cast<Py_ssize_t>(pk.total), reinterpret_cast<const char*>(pk.offsets),
+                            static_cast<Py_ssize_t>((static_cast<size_t>(pk.n) + 1) * 8));
+    for (void* p : blocks) std::free(p);
+    return out;
+}
+
 PyMethodDef methods[] = {
     {"decode_list", decode_list, METH_VARARGS, "decode_list(schema_handle, records: list[bytes], num_chunks) -> result handle"},
+    {"pack", pack, METH_VARARGS, "pack(records: list[bytes]) -> (data, offsets): the packing step alone (test hook)"},
     {nullptr, nullptr, 0, nullptr},
 };
 

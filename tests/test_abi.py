@@ -206,3 +206,27 @@ def test_specialised_kernels_compile_for_sm100a_and_use_the_copy_engine(tmp_path
     for body in (count, emit):
         assert "UBLKCP.S.G" in body and "SYNCS.ARRIVE.TRANS64" in body and "TRYWAIT" in body
     assert "UBLKCP.G.S" in emit and "UBLKCP.G.S" not in count
+
+
+def test_list_packing_matches_binaryarray_from_vec():
+    """`_native.pack` is the list[bytes] walk + gather of decode_list (pymod.cpp) into ordinary memory: values buffer +
+    i64 offsets, exactly what BinaryArray::from_vec builds at ruhvro/src/deserialize.rs:90."""
+    import numpy as np
+    ext = pr._ext()
+    rng = random.Random(3)
+    for n in (0, 1, 2, 257, 5000):
+        recs = [bytes(rng.randrange(256) for _ in range(rng.choice([0, 0, 1, 7, 64, 300]))) for _ in range(n)]
+        data, offs = ext.pack(recs)
+        want_data, want_off = po.pack_records(recs)
+        assert np.array_equal(np.frombuffer(offs, dtype=np.int64), want_off)
+        assert data == bytes(want_data)
+    big = [bytes([i & 255]) * 1024 for i in range(20_000)]            # > 8 MiB: the multi-threaded gather
+    data, offs = ext.pack(big)
+    assert data == b"".join(big) and np.frombuffer(offs, dtype=np.int64)[-1] == len(data)
+    skew = [b"x" * (12 << 20)] + [b"y"] * 1000 + [b""] * 10 + [b"z" * (3 << 20)]   # byte-balanced split, skewed sizes
+    data, offs = ext.pack(skew)
+    assert data == b"".join(skew)
+    with pytest.raises(TypeError, match="element 1 is 'str', expected 'bytes'"):
+        ext.pack([b"a", "b"])
+    with pytest.raises(TypeError):
+        ext.pack((b"a",))                                              # a list, like PyO3's Vec<Bound<PyBytes>> extraction
