@@ -247,7 +247,7 @@ def main():
         L.rv_last_timings(tbuf, 6)
         kt += np.frombuffer(tbuf, dtype=np.float32)
         launches += L.rv_last_launch_count()
-        overflow_tiles = L.rv_last_overflow_tiles()
+        overflow_tiles = L.rv_last_slow_tiles()
         L.rv_result_free(h)
     e1.record(stream)
     torch.cuda.synchronize()
@@ -296,8 +296,8 @@ def main():
     idx_bytes = 8 * (n + 1)
     emit_bytes = total_in + idx_bytes + arrow_bytes      # reads every input byte + offset, writes every Arrow byte
     count_bytes = total_in + idx_bytes                   # reads every input byte + offset
-    emit_gbs = emit_bytes / (kt[2] * 1e-3) / 1e9 if kt[2] > 0 else 0.0
-    count_gbs = count_bytes / (kt[0] * 1e-3) / 1e9 if kt[0] > 0 else 0.0
+    emit_gbs = emit_bytes / (kt[0] * 1e-3) / 1e9 if kt[0] > 0 else 0.0
+    count_gbs = 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -343,12 +343,11 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": total_in + idx_bytes, "d2h_bytes_per_step": buffer_bytes,
                 "ms_per_step": 1000.0 * e2e_s / steps, "h2d_ms": h2d_ms / steps, "d2h_ms": d2h_ms / steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "rvj_emit" if pr.last_walker() == "jit" else "emit_kernel", "achieved": emit_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": emit_gbs / peak, "traffic": traffic, "algorithmic_bytes": emit_bytes, "kernel_ms": kt[2],
-                     "peak_source": peak_src,
-                     "count_kernel": {"achieved": count_gbs, "frac": count_gbs / peak, "algorithmic_bytes": count_bytes, "kernel_ms": kt[0]},
-                     "scan_kernel_ms": kt[1], "null_count_kernel_ms": kt[3], "walker": pr.last_walker(),
-                     "overflow_tiles_per_step": overflow_tiles},
+        "roofline": {"bound": "hbm", "kernel": "rvj_fused" if pr.last_walker() == "jit" else "fused_kernel", "achieved": emit_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": emit_gbs / peak, "traffic": traffic, "algorithmic_bytes": emit_bytes, "kernel_ms": kt[0],
+                     "peak_source": peak_src, "path_frac": emit_bytes / (ms_total / steps * 1e-3) / 1e9 / peak,
+                     "extra_pass_ms": kt[1], "null_count_kernel_ms": kt[3], "walker": pr.last_walker(),
+                     "slow_tiles_per_step": overflow_tiles},
         "clocks": sampler.summary(),
     }
     if cpu is not None:

@@ -83,9 +83,11 @@ rv_status rv_decode_host(const rv_schema* s, const uint8_t* data, const int64_t*
                          int64_t num_chunks, rv_result** out);
 
 /* Device variant (the benchmark / pipeline path): `d_data`/`d_offsets` are device pointers on the
- * current CUDA device, `d_data` 16-byte aligned; work is enqueued on `cuda_stream` (a
+ * current CUDA device, `d_data` 16-byte aligned and readable for at least 16 bytes past
+ * d_data[d_offsets[n]] (tiles are staged in 16-byte vectors); work is enqueued on `cuda_stream` (a
  * cudaStream_t; NULL = default stream) and the call returns after the kernels completed.  The
- * batches stay in HBM until rv_result_to_host(). */
+ * batches stay in HBM until rv_result_to_host(); their buffers are sized from what earlier calls on
+ * the same schema handle needed, so they may carry a few per cent of slack between them. */
 rv_status rv_decode_device(const rv_schema* s, const uint8_t* d_data, const int64_t* d_offsets, int64_t n,
                            int64_t num_chunks, void* cuda_stream, rv_result** out);
 
@@ -138,12 +140,17 @@ rv_status rv_dev_concat_bits(uint32_t* d_dst_words, int64_t dst_bit, const uint3
 void* rv_host_alloc(size_t bytes); /* pinned host memory (cudaHostAlloc); NULL on failure */
 void rv_host_free(void* p);
 
-/* Per-call kernel timings of the calling thread's last decode, in milliseconds (CUDA events on
- * the launch stream): [0] count_kernel, [1] scan_kernel, [2] emit_kernel, [3] null_count_kernel,
+/* Per-call timings of the calling thread's last decode, in milliseconds (CUDA events on the launch stream):
+ * [0] the fused decode kernel (the pass that produced the batches), [1] an extra measuring pass (the first call on a
+ * schema, or a call whose data outgrew the planned buffers; 0 otherwise), [2] unused, [3] null_count_kernel,
  * [4] H2D copy, [5] D2H copy.  Returns how many entries were written (<= cap). */
 int rv_last_timings(float* out_ms, int cap);
 /* Number of kernels the last decode on this thread launched. */
 int rv_last_launch_count(void);
+/* Passes of the fused kernel the last decode on this thread needed: 1 in steady state, 2 when it had to measure first. */
+int rv_last_passes(void);
+/* Drops what the schema handle learned about output sizes from earlier calls (the next call measures again). */
+void rv_schema_forget_stats(const rv_schema* s);
 
 /* Which record walker the last decode on this thread ran: "jit" (schema-specialised kernels compiled
  * with NVRTC for the device's architecture) or "interp" (the statically compiled generic kernels).
@@ -152,9 +159,9 @@ const char* rv_last_walker(void);
 /* Why the schema-specialised kernels are / are not in use for this schema ("ok", the NVRTC log, ...).
  * The returned string is valid until the calling thread's next library call. */
 const char* rv_schema_jit_status(const rv_schema* s);
-/* Tiles of the last decode on this thread that did not fit the shared-memory window of the specialised
- * kernels and were handled by the interpreter overflow pass (diagnostics). */
-long long rv_last_overflow_tiles(void);
+/* Tiles of the last decode on this thread that did not fit the shared-memory windows and were walked in global
+ * memory instead (slow path inside the same kernel; diagnostics). */
+long long rv_last_slow_tiles(void);
 /* 1 / 0: use / do not use the schema-specialised kernels from now on; -1: follow the RV_JIT environment variable. */
 void rv_set_jit_enabled(int enabled);
 

@@ -90,7 +90,10 @@ def _load():
     L.rv_host_free.restype = None
     L.rv_last_timings.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_int]
     L.rv_last_launch_count.restype = ctypes.c_int
-    L.rv_last_overflow_tiles.restype = ctypes.c_longlong
+    L.rv_last_slow_tiles.restype = ctypes.c_longlong
+    L.rv_last_passes.restype = ctypes.c_int
+    L.rv_schema_forget_stats.argtypes = [vp]
+    L.rv_schema_forget_stats.restype = None
     L.rv_last_walker.restype = cp
     L.rv_set_jit_enabled.argtypes = [ctypes.c_int]
     L.rv_set_jit_enabled.restype = None

@@ -44,8 +44,8 @@ struct WalkCtx {
     uint32_t ptrs_soff;    // device emit: offset inside rv_smem of the CTA's copy of that table (0: none)
     const int32_t* sym_off;
     const uint8_t* sym_bytes;
-    bool stage_on;         // emit: Utf8 bytes go to the shared-memory staging area
-    uint32_t stage_soff;   // offset of the staging area inside rv_smem
+    uint32_t stage_soff;   // SM: offset of the Utf8 staging area inside rv_smem (emit assembles strings there; the
+                           // global-memory context writes them straight to their Arrow buffers)
     const uint32_t* stage_adj;  // [stream]: staging offset of the stream's region minus the tile base
     uint32_t row0;         // chunk-local row of this record
     bool in_range;         // the lane owns a record
@@ -309,26 +309,16 @@ __device__ __forceinline__ void copy_smem_words(const uint32_t d, const uint32_t
 #endif
 
 // ---- Utf8 leaves ----------------------------------------------------------------------------
-// Destination of string bytes: the CTA's shared-memory staging area (written out with coalesced
-// 128-bit stores by the kernel afterwards) or, when the tile does not fit, global memory directly.
-// RV_EMIT_STAGED_ONLY (set by the generated kernels): the walker is only ever run on tiles whose strings fit
-// the staging area — emit_body hands the others to the interpreter pass — so the fallback is compiled out.
+// Destination of string bytes: the CTA's shared-memory staging area (written out by the kernel afterwards through
+// bulk stores) when the record is walked in shared memory; a tile that does not fit is walked in global memory
+// (WalkCtx<false>) and writes its strings straight to the Arrow data buffers.
 template <class C>
 RV_HD void copy_from_record(C& c, int slot_b, int stream, uint32_t o, uint32_t s, uint32_t len) {
 #if defined(__CUDA_ARCH__)
-#if defined(RV_EMIT_STAGED_ONLY)
-    if (true) {
-#else
-    if (c.stage_on) {
-#endif
-        const uint32_t d = c.stage_soff + c.stage_adj[stream] + o;
-        if (C::kShared) {
+    if constexpr (C::kShared) {
 #if !defined(RV_ABL_NOCOPY)  // (RV_ABL_*: timing ablations for tools/sweep_jit.py — they produce wrong output)
-            copy_smem_words(d, c.soff + s, len);
+        copy_smem_words(c.stage_soff + c.stage_adj[stream] + o, c.soff + s, len);
 #endif
-        } else {
-            for (uint32_t i = 0; i < len; ++i) rv_smem[d + i] = uint8_t(ld_u8(c, s + i));
-        }
         return;
     }
 #endif
@@ -340,11 +330,7 @@ RV_HD void copy_from_record(C& c, int slot_b, int stream, uint32_t o, uint32_t s
 template <class C>
 RV_HD void copy_from_symbols(C& c, int slot_b, int stream, uint32_t o, const uint8_t* src, uint32_t len) {
 #if defined(__CUDA_ARCH__)
-#if defined(RV_EMIT_STAGED_ONLY)
-    if (true) {
-#else
-    if (c.stage_on) {
-#endif
+    if constexpr (C::kShared) {
         const uint32_t d = c.stage_soff + c.stage_adj[stream] + o;
         for (uint32_t i = 0; i < len; ++i) rv_smem[d + i] = src[i];
         return;

@@ -1,18 +1,28 @@
-// Kernel bodies of the decode, templated over the walker (InterpWalker or a generated,
-// schema-specialised walker).  Device-only; compiled by nvcc (kernels.cu) and by NVRTC (jit.cpp).
+// Kernel body of the decode: ONE fused pass per 256-record tile, templated over the walker (InterpWalker or a
+// generated, schema-specialised walker).  Device-only; compiled by nvcc (kernels.cu) and by NVRTC (jit.cpp).
 //
-//   count_body  one CTA per 256-record tile: one TMA bulk copy (cp.async.bulk + mbarrier) stages the tile's
-//               contiguous byte window in shared memory, every lane COUNT-walks its record (full validation),
-//               a warp-per-stream scan turns the lane counts into in-tile prefixes -> lane_off, tile_agg.
-//   emit_body   same staging; the lanes' cursors (tile base from scan_kernel + in-tile prefix from count) are
-//               loaded while the window is in flight -> EMIT walk.  Utf8 bytes are assembled per column in a
-//               shared-memory staging area and leave through TMA bulk stores (16-byte aligned body) plus a few
-//               head/tail bytes; fixed-width values / offsets are stored row-aligned; space-0 validity is one
-//               ballot word per warp.
+//   fused_body  one CTA per tile, tiles taken in blockIdx order:
+//     1. one TMA bulk copy (cp.async.bulk + mbarrier) stages the tile's contiguous byte window in shared memory;
+//     2. every lane COUNT-walks its record (full validation) -> per-stream counts;
+//     3. a warp-per-stream scan turns the lane counts into in-tile prefixes and the tile's totals;
+//     4. the totals are chained across tiles with a decoupled look-back (Merrill & Garland): each (stream, tile) has a
+//        64-bit status word {flag, value} in global memory; a tile publishes its aggregate, sums its predecessors'
+//        aggregates back to the nearest published inclusive prefix, then publishes its own inclusive prefix.  Every
+//        output batch (chunk) is its own chain, so Arrow offsets restart at 0 per batch;
+//     5. the same CTA EMIT-walks the still-resident window: fixed-width values / offsets are stored row-aligned,
+//        space-0 validity is one ballot word per warp, Utf8 bytes are assembled per column in a shared-memory staging
+//        area and leave through TMA bulk stores (16-byte aligned body) plus a few head/tail bytes.
+//   The input is read from HBM once and nothing but the Arrow buffers (and 8 bytes per stream per tile of scan
+//   status) is written.
+//
+//   Output capacity.  Buffers whose size depends on the data (string bytes, list child rows) are sized by the host
+//   from what earlier calls on the same schema needed (p.caps); a tile whose range would not fit raises CW_OVER,
+//   skips its emit and still publishes, so the pass ends with exact totals and the host repeats it once with an
+//   exact-size arena.  p.count_only (the first call on a schema) skips every emit.
 //
 // Shared-memory map (dynamic, rv_smem; smem_map() in dev_types.h):
-//   [nodes n_nodes*32][wtot S*8*4 (emit: tile bases)][tot (S+1)*4][adj S*4][mbar 8][ptrs n_slots*8][cur S*256*4][in: smem_data_cap][out: smem_stage_cap]
-//   (register-cursor walkers: `cur` overlays `in`)
+//   [nodes n_nodes*32][ttot (S+1)*4][tbase S*4][adj S*4][flags 16][mbar 8][ptrs n_slots*8][cur S*256*4 (interpreter)]
+//   [in: smem_data_cap + pad][stage: smem_stage_cap]        (register-cursor walkers: the scan area overlays `stage`)
 #pragma once
 #include "dev_core.cuh"
 
@@ -65,10 +75,8 @@ constexpr int kPrefetchLane = 32;  // the lane (first of warp 1) that carries th
 
 // ---- TMA (bulk async copy) staging of the input window -----------------------------------------------
 // One thread hands the whole window to the copy engine (cp.async.bulk global -> shared, completion counted in
-// bytes on an mbarrier) instead of every thread moving its share through registers (LDG.128 + STS.128): the
-// prologue loses ~40 issue slots per thread and the loads no longer occupy registers.
+// bytes on an mbarrier) instead of every thread moving its share through registers (LDG.128 + STS.128).
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-#if !defined(RV_NO_TMA_STAGE)
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t arrivals) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(arrivals) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy
@@ -89,42 +97,65 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
         "RV_DONE:\n"
         "}" ::"r"(mbar), "r"(parity) : "memory");
 }
-#endif
+
+// ---- scan status words (decoupled look-back) -----------------------------------------------------------
+// {flag:2, value:62} in one 64-bit word, written and read with single relaxed gpu-scope accesses: flag and
+// value can never be seen torn, so no fences are needed around them.
+constexpr unsigned long long kStAgg = 1ull << 62;      // value = this tile's total
+constexpr unsigned long long kStPrefix = 2ull << 62;   // value = total of this tile and every earlier tile of the chunk
+constexpr unsigned long long kStMask = (1ull << 62) - 1ull;
+
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Whole warp: the sum of the totals of tiles [first, tile) of one stream.  Lane l inspects tile (t - l); the warp
+// walks back 32 tiles at a time until it meets a published inclusive prefix (tiles before `first` count as one).
+__device__ __forceinline__ unsigned long long look_back(const unsigned long long* st, const int tile, const int first) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long excl = 0;
+    int t = tile - 1;
+    for (;;) {
+        const int mine = t - lane;
+        const bool real = mine >= first;  // tiles before the chain count as one virtual tile with inclusive prefix 0
+        unsigned long long v;
+        do { v = real ? ld_state(st + mine) : kStPrefix; } while (__any_sync(0xFFFFFFFFu, (v >> 62) == 0ull));
+        const unsigned has = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2ull);
+        const int pl = has ? __ffs(int(has)) - 1 : 32;  // nearest tile that already knows its prefix
+        unsigned long long c = lane <= pl ? (v & kStMask) : 0ull;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+        excl += c;
+        if (has) break;
+        t -= 32;
+    }
+    return excl;
+}
 
 // Loads the plan and the tile's byte window into shared memory.
-// EMIT: the lanes' cursors (tile base + in-tile prefix) and, further down, zeroing of the Utf8 staging
-// area are issued here too, so their latency overlaps the input loads.
-template <bool EMIT, class W>
-__device__ __forceinline__ TileWindow stage_in(const DecodeParams& p, const Tile& t, const int tile_id, const SmemMap& m, typename W::Cur& q) {
+template <class W>
+__device__ __forceinline__ TileWindow stage_in(const DecodeParams& p, const Tile& t, const int tile_id, const SmemMap& m) {
     const int tid = threadIdx.x;
-#if !defined(RV_NO_TMA_STAGE)
     if (tid == 0) mbar_init(smem_addr(rv_smem + m.mbar), 1);
-#endif
     if (p.n_nodes) {
         uint4* dn = reinterpret_cast<uint4*>(rv_smem + m.nodes);
         for (int i = tid; i < p.n_nodes * 2; i += kBlock) dn[i] = __ldg(reinterpret_cast<const uint4*>(p.nodes) + i);
     }
-    uint32_t* cur = reinterpret_cast<uint32_t*>(rv_smem + m.cur);
-    if (EMIT) {
-        // this chunk's Arrow buffer pointers (see buf_ptr)
+    if (p.bufs) {  // this chunk's Arrow buffer pointers (see buf_ptr)
         void** sp = reinterpret_cast<void**>(rv_smem + m.ptrs);
         void* const* gp = p.bufs + size_t(t.chunk) * p.n_slots;
         for (int i = tid; i < p.n_slots; i += kBlock) sp[i] = gp[i];
-        const uint32_t* lo = p.lane_off + size_t(tile_id) * p.n_streams * kBlock;
-        if constexpr (W::kRegCursors) {
-#pragma unroll
-            for (int s = 0; s < W::kStreams; ++s)
-                q.v[s] = __ldg(lo + s * kBlock + tid) + __ldg(p.tile_base + size_t(s) * p.n_tiles + tile_id);
-        } else {
-            for (int s = 0; s < p.n_streams; ++s)
-                cur[s * kBlock + tid] = __ldg(lo + s * kBlock + tid) + __ldg(p.tile_base + size_t(s) * p.n_tiles + tile_id);
-        }
-        uint4* z = reinterpret_cast<uint4*>(rv_smem + m.out);
-        for (uint32_t i = tid; i < (p.smem_stage_cap >> 4); i += kBlock) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    } else if constexpr (!W::kRegCursors) {
+    }
+    if constexpr (!W::kRegCursors) {
+        uint32_t* cur = reinterpret_cast<uint32_t*>(rv_smem + m.cur);
         for (int s = 0; s < p.n_streams; ++s) cur[s * kBlock + tid] = 0;
     }
-    (void)cur;
+    if (tid == 0) *reinterpret_cast<uint32_t*>(rv_smem + m.flags) = 0u;
     TileWindow w;
     // One round trip: the tile's bounds, this lane's record bounds and (one lane) the bounds of the tile a
     // later CTA will work on are all requested before anything waits.
@@ -137,41 +168,36 @@ __device__ __forceinline__ TileWindow stage_in(const DecodeParams& p, const Tile
     }
     w.f0 = w.f1 = -1;
     const int64_t ft = int64_t(tile_id) + p.prefetch_dist;
-    if (p.prefetch_dist > 0 && !p.tile_list && ft < p.n_tiles) {
+    if (p.prefetch_dist > 0 && ft < p.n_tiles) {
         const Tile f = tile_of(p, int(ft));
         if (tid < 17 && f.r0 + 16 * tid <= p.n) l2_prefetch_line(p.offsets + f.r0 + 16 * tid);  // the 2 KiB (+8 B) of offsets of that tile
         if (tid == kPrefetchLane) {
             w.f0 = __ldg(p.offsets + f.r0);
             w.f1 = __ldg(p.offsets + f.r0 + f.nrec);
         }
-        if (EMIT && tid == kPrefetchLane + 1)
-            l2_prefetch_bulk(p.lane_off + size_t(ft) * p.n_streams * kBlock, uint32_t(p.n_streams) * kBlock * 4u);
     }
     const int64_t span = w.t1 - w.t0;
     w.mis = uint32_t(reinterpret_cast<uintptr_t>(p.data + w.t0) & 15u);
     w.staged = span >= 0 && uint64_t(span) + w.mis <= uint64_t(p.smem_data_cap);
     w.tma = false;
     if (w.staged) {
+        // (the last vector may read up to 15 bytes past offsets[n]: rv_decode_device documents the padding)
         const uint4* g = reinterpret_cast<const uint4*>(p.data + w.t0 - w.mis);
         const int nvec = int((span + w.mis + 15) >> 4);
-        uint4* d = reinterpret_cast<uint4*>(rv_smem + m.in);
-#if !defined(RV_NO_TMA_STAGE)
         w.tma = nvec > 0;
-        if (w.tma && tid == 0) bulk_load(smem_addr(d), g, uint32_t(nvec) << 4, smem_addr(rv_smem + m.mbar));
-#else
-        for (int i = tid; i < nvec; i += kBlock) d[i] = __ldg(g + i);
-#endif
+        if (w.tma && tid == 0) bulk_load(smem_addr(rv_smem + m.in), g, uint32_t(nvec) << 4, smem_addr(rv_smem + m.mbar));
+    }
+    if (tid == 0) {  // window sizing of later calls: the largest tile seen, the input's byte span
+        if (span > 0 && static_cast<unsigned long long>(span) > p.ctrl[CW_MAX_SPAN]) atomicMax(p.ctrl + CW_MAX_SPAN, static_cast<unsigned long long>(span));
+        if (tile_id == 0) p.ctrl[CW_IN_FIRST] = static_cast<unsigned long long>(w.t0);
+        if (tile_id == p.n_tiles - 1) p.ctrl[CW_IN_LAST] = static_cast<unsigned long long>(w.t1);
     }
     return w;
 }
 
 // After the CTA barrier that follows stage_in (which also publishes the mbarrier's initialisation).
 __device__ __forceinline__ void wait_window(const TileWindow& w, const SmemMap& m) {
-#if !defined(RV_NO_TMA_STAGE)
     if (w.tma) mbar_wait(smem_addr(rv_smem + m.mbar), 0);
-#else
-    (void)w; (void)m;
-#endif
 }
 
 template <class C>
@@ -186,8 +212,7 @@ __device__ __forceinline__ int64_t init_ctx(C& c, const DecodeParams& p, const T
     c.err = 0;
     c.pm = 0;
     c.usel = 0;
-    c.stage_on = false;
-    c.stage_soff = m.out;
+    c.stage_soff = m.stage;
     c.stage_adj = reinterpret_cast<const uint32_t*>(rv_smem + m.adj);
     c.in_range = tid < t.nrec;
     c.row0 = uint32_t(t.local_tile) * kBlock + tid;
@@ -211,7 +236,7 @@ __device__ __forceinline__ int64_t init_ctx(C& c, const DecodeParams& p, const T
 }
 
 __device__ __forceinline__ void report(const DecodeParams& p, int64_t record, uint32_t code) {
-    atomicMin(p.err, (static_cast<unsigned long long>(record) << 8) | code);
+    atomicMin(p.ctrl + CW_ERR, (static_cast<unsigned long long>(record) << 8) | code);
 }
 
 // The look-ahead lane asks L2 for the input window of the tile `prefetch_dist` ahead (its bounds arrived
@@ -225,8 +250,10 @@ __device__ __forceinline__ void prefetch_window(const DecodeParams& p, const Til
 }
 
 // ---- count ----------------------------------------------------------------------------------
+// Returns this lane's error code.  (Never inlined for the global-memory window: that instantiation only runs for
+// tiles that do not fit shared memory and must not cost the common path registers.)
 template <class W, bool SM>
-__device__ __forceinline__ void count_walk(const DecodeParams& p, const Tile& t, const SmemMap& m, const TileWindow& w, typename W::Cur& q) {
+__device__ __forceinline__ uint32_t count_walk(const DecodeParams& p, const Tile& t, const SmemMap& m, const TileWindow& w, typename W::Cur& q) {
     WalkCtx<SM> c;
     const int64_t r = init_ctx(c, p, t, m, w);
     if constexpr (W::kRegCursors) {
@@ -237,39 +264,147 @@ __device__ __forceinline__ void count_walk(const DecodeParams& p, const Tile& t,
     W::template walk<WM_COUNT>(c, p.n_nodes, q);
 #endif
     if (c.in_range && c.err) report(p, r, c.err);
+    return c.in_range ? c.err : 0u;
+}
+// Everything by value: a reference parameter of a function that is not inlined would force the caller's copy (the
+// kernel parameters, the cursors) out of registers into local memory for the whole kernel.
+template <class W>
+struct CountOut { typename W::Cur q; uint32_t err; };
+template <class W>
+__device__ __noinline__ CountOut<W> count_walk_global(const DecodeParams p, const Tile t, const SmemMap m, const TileWindow w) {
+    CountOut<W> o;
+    o.err = count_walk<W, false>(p, t, m, w, o.q);
+    return o;
 }
 
-// GENERIC = the walker can read records straight from global memory (interpreter).  A specialised
-// walker is only instantiated for the shared-memory window; tiles that do not fit are handed to the
-// interpreter kernels through p.overflow.
-template <class W, bool GENERIC>
-__device__ __forceinline__ void count_body(const DecodeParams& p, const int tile_id) {
+// ---- emit: staging map ------------------------------------------------------------------------
+// Stream s's Utf8 bytes of this tile occupy [tbase, tbase + ttot) of its Arrow data buffer; in shared memory its
+// region starts at a 16-byte boundary plus the destination's misalignment, so the write-out can use aligned 16-byte
+// pieces.  Warp 0 computes the map with a shuffle scan once the look-back delivered the tile's bases.
+// flags bit 1 <- the tile's strings fit the staging area.
+__device__ __forceinline__ void stage_map(const DecodeParams& p, const Tile& t, const SmemMap& m) {
+    const uint32_t* tbase = reinterpret_cast<const uint32_t*>(rv_smem + m.tbase);
+    const uint32_t* ttot = reinterpret_cast<const uint32_t*>(rv_smem + m.ttot);
+    uint32_t* adj = reinterpret_cast<uint32_t*>(rv_smem + m.adj);
+    const int lane = threadIdx.x & 31;
+    uint32_t carry = 0;
+    for (int s0 = 0; s0 < p.n_streams; s0 += 32) {
+        const int s = s0 + lane;
+        uint32_t tb = 0, ga = 0, region = 0;
+        int slot = -1;
+        if (s < p.n_streams) {
+            tb = tbase[s];
+            slot = p.stream_slot[s];
+            if (slot >= 0) {
+                const uint8_t* b = *reinterpret_cast<uint8_t* const*>(rv_smem + m.ptrs + uint32_t(slot) * 8u);
+                ga = uint32_t(reinterpret_cast<uintptr_t>(b + tb) & 15u);
+                region = (ttot[s] + ga + 15u) & ~15u;
+            }
+        }
+        uint32_t incl = region;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += u;
+        }
+        if (s < p.n_streams) adj[s] = slot >= 0 ? (carry + incl - region + ga) - tb : 0u;  // staging offset of chunk-relative byte o = adj + o
+        carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    if (lane == 0 && (p.n_utf8 == 0 || (p.smem_stage_cap > 0 && carry <= p.smem_stage_cap))) atomicOr(reinterpret_cast<uint32_t*>(rv_smem + m.flags), 2u);
+    (void)t;
+}
+
+// ---- emit -----------------------------------------------------------------------------------
+template <class W, bool SM>
+__device__ __forceinline__ void emit_walk(const DecodeParams& p, const Tile& t, const SmemMap& m, const TileWindow& w, typename W::Cur& q) {
+    WalkCtx<SM> c;
+    (void)init_ctx(c, p, t, m, w);
+    const int tid = threadIdx.x;
+    // offsets[0] = 0 of every offsets buffer of this chunk (first tile of the chunk only)
+    if (t.local_tile == 0) {
+        if (p.n_nodes) {
+            for (int i = tid; i < p.n_nodes; i += kBlock) {
+                const DNode nd = c.nodes[i];
+                if (nd.kind == NK_STR || nd.kind == NK_ENUM || nd.kind == NK_LIST || nd.kind == NK_MAP || nd.kind == NK_BYTES)
+                    static_cast<int32_t*>(buf_ptr(c, nd.slot_a))[0] = 0;
+            }
+        } else {
+            W::zero_offsets(c, tid);
+        }
+    }
+#if !defined(RV_ABL_NOWALK)
+    W::template walk<WM_EMIT>(c, p.n_nodes, q);
+#endif
+}
+template <class W>
+__device__ __noinline__ void emit_walk_global(const DecodeParams p, const Tile t, const SmemMap m, const TileWindow w, typename W::Cur q) {
+    emit_walk<W, false>(p, t, m, w, q);
+}
+
+// Coalesced write-out of the staged Utf8 bytes, one warp per stream at a time.
+__device__ __forceinline__ void stage_write_out(const DecodeParams& p, const SmemMap& m) {
+    const uint32_t* tbase = reinterpret_cast<const uint32_t*>(rv_smem + m.tbase);
+    const uint32_t* ttot = reinterpret_cast<const uint32_t*>(rv_smem + m.ttot);
+    const uint32_t* adj = reinterpret_cast<const uint32_t*>(rv_smem + m.adj);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staged bytes -> visible to the copy engine
+    __syncthreads();
+    for (int s = warp; s < p.n_streams; s += kWarps) {
+        const int slot = p.stream_slot[s];
+        const uint32_t n = ttot[s];
+        if (slot < 0 || n == 0) continue;
+        const uint32_t tb = tbase[s];
+        uint8_t* g = *reinterpret_cast<uint8_t* const*>(rv_smem + m.ptrs + uint32_t(slot) * 8u) + tb;
+        const uint32_t so = m.stage + adj[s] + tb;  // rv_smem offset of the region's first byte
+        const uint32_t head = min(n, (16u - uint32_t(reinterpret_cast<uintptr_t>(g) & 15u)) & 15u);
+        for (uint32_t i = lane; i < head; i += 32) g[i] = rv_smem[so + i];
+        const uint32_t nvec = (n - head) >> 4;
+        // the 16-byte aligned body leaves through the copy engine (shared -> global bulk store): one
+        // instruction per column instead of a store loop, and the warp does not wait for the data to drain
+        if (lane == 0 && nvec > 0)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(g + head), "r"(smem_addr(rv_smem + so + head)), "r"(nvec << 4) : "memory");
+        const uint32_t done = head + (nvec << 4);
+        for (uint32_t i = done + lane; i < n; i += 32) g[i] = rv_smem[so + i];
+    }
+    if (lane == 0) {  // shared memory must outlive the engine's reads
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
+// ---- the fused pass ---------------------------------------------------------------------------
+template <class W>
+__device__ __forceinline__ void fused_body(const DecodeParams& p, const int tile_id) {
     const Tile t = tile_of(p, tile_id);
-    const SmemMap m = smem_map(p.n_nodes, p.n_streams, p.n_slots, p.smem_data_cap, W::kRegCursors);
+    const SmemMap m = smem_map(p.n_nodes, p.n_streams, p.n_slots, p.smem_data_cap, p.smem_stage_cap, W::kRegCursors);
     typename W::Cur q;
-    const TileWindow w = stage_in<false, W>(p, t, tile_id, m, q);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const TileWindow w = stage_in<W>(p, t, tile_id, m);
     __syncthreads();
     wait_window(w, m);
-    if (w.staged) count_walk<W, true>(p, t, m, w, q);
-    else if constexpr (GENERIC) count_walk<W, false>(p, t, m, w, q);
+
+    // ---- COUNT: validation + what this record adds to every stream
+    uint32_t my_err;
+    if (w.staged) my_err = count_walk<W, true>(p, t, m, w, q);
     else {
-        if (threadIdx.x == 0) p.overflow_list[atomicAdd(p.overflow, 1)] = tile_id;
-        return;  // uniform: the whole CTA leaves
+        const CountOut<W> o = count_walk_global<W>(p, t, m, w);
+        q = o.q;
+        my_err = o.err;
     }
-    __syncthreads();
-    // CTA-wide exclusive scan of every stream's lane counts.  The per-record prefixes are saved so the
-    // emit kernel does not have to walk the records a second time just to learn where they write.
-    // One WARP scans one stream: each lane takes 8 consecutive records (two 128-bit loads), sums them
-    // serially, and a single 5-step shuffle scan joins the 32 lane totals — instead of every warp running a
-    // shuffle scan per stream plus a cross-warp pass.
+
+    // ---- CTA-wide exclusive scan of every stream's lane counts.  One WARP scans one stream: each lane takes 8
+    // consecutive records (two 128-bit loads), sums them serially, and a single 5-step shuffle scan joins the 32
+    // lane totals.
     constexpr int kPerLane = kBlock / 32;  // 4, 8, ...: a multiple of 4, so every lane moves whole uint4
     uint32_t* cur = reinterpret_cast<uint32_t*>(rv_smem + m.cur);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if constexpr (W::kRegCursors) {  // the scan area overlays the (now dead) input window
+    uint32_t* ttot = reinterpret_cast<uint32_t*>(rv_smem + m.ttot);
+    uint32_t* tbase = reinterpret_cast<uint32_t*>(rv_smem + m.tbase);
+    uint32_t* flags = reinterpret_cast<uint32_t*>(rv_smem + m.flags);
+    if constexpr (W::kRegCursors) {  // the scan area overlays the (still unused) Utf8 staging area
 #pragma unroll
         for (int s = 0; s < W::kStreams; ++s) cur[s * kBlock + tid] = q.v[s];
     }
-    __syncthreads();
+    const bool any_err = __syncthreads_or(my_err != 0u) != 0;
     for (int s = warp; s < p.n_streams; s += kWarps) {
         uint32_t* cl = cur + s * kBlock + lane * kPerLane;
         uint32_t v[kPerLane];
@@ -280,199 +415,107 @@ __device__ __forceinline__ void count_body(const DecodeParams& p, const int tile
             v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
             any |= x.x | x.y | x.z | x.w;
         }
+        uint32_t tile_total;
         // kBlock values below 2^31 / kBlock cannot overflow 31 bits; anything bigger (a tile of huge zero-width
         // lists) takes the exact 64-bit path below
         if (__any_sync(0xFFFFFFFFu, any >= (0x80000000u / uint32_t(kBlock)))) {
+            unsigned long long run = 0;
             if (lane == 0) {
                 uint32_t* cs = cur + s * kBlock;
-                unsigned long long run = 0;
                 for (int i = 0; i < kBlock; ++i) {
                     const uint32_t x = cs[i];
                     cs[i] = uint32_t(run);
                     run += x;
                 }
                 if (run > 0x7FFFFFFFull) { report(p, t.r0, E_OVERFLOW); run = 0x7FFFFFFFull; }
-                p.tile_agg[size_t(s) * p.n_tiles + tile_id] = uint32_t(run);
             }
             __syncwarp();
-            continue;
-        }
-        uint32_t tot = 0;
+            tile_total = __shfl_sync(0xFFFFFFFFu, uint32_t(run), 0);
+        } else {
+            uint32_t tot = 0;
 #pragma unroll
-        for (int i = 0; i < kPerLane; ++i) {  // lane-local exclusive prefix
-            const uint32_t x = v[i];
-            v[i] = tot;
-            tot += x;
-        }
-        uint32_t incl = tot;
+            for (int i = 0; i < kPerLane; ++i) {  // lane-local exclusive prefix
+                const uint32_t x = v[i];
+                v[i] = tot;
+                tot += x;
+            }
+            uint32_t incl = tot;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += u;
-        }
-        const uint32_t base = incl - tot;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += u;
+            }
+            const uint32_t base = incl - tot;
 #pragma unroll
-        for (int i = 0; i < kPerLane; i += 4)
-            *reinterpret_cast<uint4*>(cl + i) = make_uint4(base + v[i], base + v[i + 1], base + v[i + 2], base + v[i + 3]);
-        if (lane == 31) p.tile_agg[size_t(s) * p.n_tiles + tile_id] = incl;  // < 2^31 by construction
+            for (int i = 0; i < kPerLane; i += 4)
+                *reinterpret_cast<uint4*>(cl + i) = make_uint4(base + v[i], base + v[i + 1], base + v[i + 2], base + v[i + 3]);
+            tile_total = __shfl_sync(0xFFFFFFFFu, incl, 31);  // < 2^31 by construction
+        }
+        // publish right away: the successors' look-backs are waiting for it
+        if (lane == 0) {
+            ttot[s] = tile_total;
+            st_state(p.tile_state + size_t(s) * p.n_tiles + tile_id, (t.local_tile == 0 ? kStPrefix : kStAgg) | tile_total);
+        }
+    }
+    // ---- chain the tile totals: exclusive prefix within the chunk
+    for (int s = warp; s < p.n_streams; s += kWarps) {
+        unsigned long long base = 0;
+        const uint32_t tot = ttot[s];
+        if (t.local_tile != 0) {
+            unsigned long long* st = p.tile_state + size_t(s) * p.n_tiles;
+            base = look_back(st, tile_id, tile_id - t.local_tile);
+            if (lane == 0) st_state(st + tile_id, kStPrefix | ((base + tot) & kStMask));
+        }
+        if (lane == 0) {
+            const unsigned long long incl = base + tot;
+            const bool last = int64_t(t.local_tile + 1) * kBlock >= t.chunk_len;
+            if (last) {
+                p.ctrl[CW_CHUNK_TOT + size_t(t.chunk) * p.n_streams + s] = incl;
+                if (incl > 0x7FFFFFFFull) report(p, int64_t(t.chunk) * p.chunk_rows, E_OVERFLOW);
+            }
+            const unsigned long long cap = p.caps ? static_cast<unsigned long long>(p.caps[size_t(t.chunk) * p.n_streams + s]) : 0ull;
+            if (incl > cap && !p.count_only) {  // this tile's range does not fit the buffer the host sized: exact totals, then a repeat
+                atomicOr(flags, 1u);
+                if (p.ctrl[CW_OVER] == 0ull) atomicMax(p.ctrl + CW_OVER, 1ull);
+            }
+            tbase[s] = uint32_t(base > 0x7FFFFFFFull ? 0x7FFFFFFFull : base);
+        }
     }
     __syncthreads();
-    uint32_t* lo = p.lane_off + size_t(tile_id) * p.n_streams * kBlock;
+    if (warp == 0 && p.n_utf8 > 0) {  // staging need of this tile (upper bound: 31 bytes of alignment per column)
+        uint32_t need = 0;
+        for (int s = lane; s < p.n_streams; s += 32)
+            if (p.stream_slot[s] >= 0) need += ttot[s] + 31u;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) need += __shfl_xor_sync(0xFFFFFFFFu, need, d);
+        if (lane == 0 && static_cast<unsigned long long>(need) > p.ctrl[CW_MAX_UTF8]) atomicMax(p.ctrl + CW_MAX_UTF8, static_cast<unsigned long long>(need));
+    }
+    if (p.count_only || any_err || (flags[0] & 1u)) return;  // uniform: the whole CTA leaves
+
+    // ---- cursors: tile base + in-tile prefix; staging map (warp 0) while the rest zero the staging area
     if constexpr (W::kRegCursors) {
 #pragma unroll
-        for (int s = 0; s < W::kStreams; ++s) lo[s * kBlock + tid] = cur[s * kBlock + tid];
+        for (int s = 0; s < W::kStreams; ++s) q.v[s] = cur[s * kBlock + tid] + tbase[s];
     } else {
-        for (int s = 0; s < p.n_streams; ++s) lo[s * kBlock + tid] = cur[s * kBlock + tid];
+        for (int s = 0; s < p.n_streams; ++s) cur[s * kBlock + tid] += tbase[s];
     }
-    prefetch_window(p, w);
-}
-
-// ---- emit: staging map ------------------------------------------------------------------------
-// Stream s's Utf8 bytes of this tile occupy [tile_base, tile_base + tot) of its Arrow data buffer; in shared
-// memory its region starts at a 16-byte boundary plus the destination's misalignment, so the write-out can use
-// aligned uint4.  Warp 0 computes the map with a shuffle scan.  Its inputs do not depend on the tile's bytes, so
-// they are requested at the very top of the CTA (map_preload) and consumed after the window loads were issued
-// (map_finish): one barrier and one exposed L2 round trip less than computing the map after the window arrived.
-struct MapPre { uint32_t tb, tt, ga, region; int slot; };
-
-__device__ __forceinline__ MapPre map_preload(const DecodeParams& p, const Tile& t, const int tile_id, const int s) {
-    MapPre r{0u, 0u, 0u, 0u, -1};
-    if (s < p.n_streams) {
-        r.tb = __ldg(p.tile_base + size_t(s) * p.n_tiles + tile_id);
-        r.tt = __ldg(p.tile_agg + size_t(s) * p.n_tiles + tile_id);
-        r.slot = p.stream_slot[s];
-        if (r.slot >= 0) {
-            const uint8_t* b = static_cast<const uint8_t*>(p.bufs[size_t(t.chunk) * p.n_slots + r.slot]);
-            r.ga = uint32_t(reinterpret_cast<uintptr_t>(b + r.tb) & 15u);
-            r.region = (r.tt + r.ga + 15u) & ~15u;
-        }
+    if constexpr (W::kRegCursors) __syncthreads();  // every lane read its prefixes: the staging area may be overwritten
+    if (warp == 0) stage_map(p, t, m);
+    if (w.staged && p.n_utf8 > 0) {
+        uint4* z = reinterpret_cast<uint4*>(rv_smem + m.stage);
+        for (uint32_t i = tid; i < (p.smem_stage_cap >> 4); i += kBlock) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
-    return r;
-}
-
-// warp 0 only
-__device__ __forceinline__ void map_finish(const DecodeParams& p, const Tile& t, const int tile_id, const SmemMap& m, MapPre pre) {
-    uint32_t* tbase = reinterpret_cast<uint32_t*>(rv_smem + m.wtot);
-    uint32_t* tot = reinterpret_cast<uint32_t*>(rv_smem + m.tot);
-    uint32_t* adj = reinterpret_cast<uint32_t*>(rv_smem + m.adj);
-    const int lane = threadIdx.x & 31;
-    uint32_t carry = 0;
-    for (int s0 = 0; s0 < p.n_streams; s0 += 32) {
-        const int s = s0 + lane;
-        if (s0 > 0) pre = map_preload(p, t, tile_id, s);
-        uint32_t incl = pre.region;
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += u;
-        }
-        if (s < p.n_streams) {
-            tbase[s] = pre.tb;
-            tot[s] = pre.tt;
-            adj[s] = pre.slot >= 0 ? (carry + incl - pre.region + pre.ga) - pre.tb : 0u;  // staging offset of chunk-relative byte o = adj + o
-        }
-        carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
-    }
-    if (lane == 0) tot[p.n_streams] = (p.smem_stage_cap > 0 && carry <= p.smem_stage_cap) ? 1u : 0u;
-}
-
-// ---- emit -----------------------------------------------------------------------------------
-template <class W, bool SM>
-__device__ __forceinline__ void emit_walks(const DecodeParams& p, const Tile& t, const int tile_id, const SmemMap& m, const TileWindow& w, typename W::Cur& q) {
-    WalkCtx<SM> c;
-    (void)init_ctx(c, p, t, m, w);
-    uint32_t* tbase = reinterpret_cast<uint32_t*>(rv_smem + m.wtot);  // reused: [S] tile bases, then [S] region alignments
-    uint32_t* tot = reinterpret_cast<uint32_t*>(rv_smem + m.tot);
-    uint32_t* adj = reinterpret_cast<uint32_t*>(rv_smem + m.adj);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // (each record's first row / first byte per stream was loaded into `cur` by stage_in: the chunk-relative
-    // tile base from scan_kernel + the record's prefix inside the tile from the count kernel; the staging map
-    // was written by warp 0 before the barrier that published the window)
-    const bool stage_on = p.n_streams > 0 && tot[p.n_streams] != 0;
-    // offsets[0] = 0 of every offsets buffer of this chunk (first tile of the chunk only)
-    if (t.local_tile == 0) {
-        if (p.n_nodes) {
-            for (int i = tid; i < p.n_nodes; i += kBlock) {
-                const DNode nd = c.nodes[i];
-                if (nd.kind == NK_STR || nd.kind == NK_ENUM || nd.kind == NK_LIST || nd.kind == NK_MAP)
-                    static_cast<int32_t*>(buf_ptr(c, nd.slot_a))[0] = 0;
-            }
-        } else {
-            W::zero_offsets(c, tid);
-        }
-    }
-    c.stage_on = stage_on;
-#if !defined(RV_ABL_NOWALK)
-    W::template walk<WM_EMIT>(c, p.n_nodes, q);
-#endif
-    prefetch_window(p, w);
-
-#if defined(RV_ABL_NOWRITEOUT)
-    if (false) {
-#else
-    if (stage_on) {  // coalesced write-out of the staged Utf8 bytes, one warp per stream at a time
-#endif
-#if !defined(RV_NO_TMA_STORE)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staged bytes -> visible to the copy engine
-#endif
-        __syncthreads();
-        for (int s = warp; s < p.n_streams; s += kWarps) {
-            const int slot = p.stream_slot[s];
-            const uint32_t n = tot[s];
-            if (slot < 0 || n == 0) continue;
-            const uint32_t tb = tbase[s];
-            uint8_t* g = static_cast<uint8_t*>(buf_ptr(c, slot)) + tb;
-            const uint32_t so = m.out + adj[s] + tb;  // rv_smem offset of the region's first byte
-            const uint32_t head = min(n, (16u - uint32_t(reinterpret_cast<uintptr_t>(g) & 15u)) & 15u);
-            for (uint32_t i = lane; i < head; i += 32) g[i] = rv_smem[so + i];
-            const uint32_t nvec = (n - head) >> 4;
-#if !defined(RV_NO_TMA_STORE)
-            // the 16-byte aligned body leaves through the copy engine (shared -> global bulk store): one
-            // instruction per column instead of a store loop, and the warp does not wait for the data to drain
-            if (lane == 0 && nvec > 0)
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                             ::"l"(g + head), "r"(smem_addr(rv_smem + so + head)), "r"(nvec << 4) : "memory");
-#else
-            const uint4* sv = reinterpret_cast<const uint4*>(rv_smem + so + head);
-            uint4* gv = reinterpret_cast<uint4*>(g + head);
-            for (uint32_t i = lane; i < nvec; i += 32) gv[i] = sv[i];
-#endif
-            const uint32_t done = head + (nvec << 4);
-            for (uint32_t i = done + lane; i < n; i += 32) g[i] = rv_smem[so + i];
-        }
-#if !defined(RV_NO_TMA_STORE)
-        if (lane == 0) {  // shared memory must outlive the engine's reads
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        }
-#endif
-    }
-}
-
-template <class W, bool GENERIC>
-__device__ __forceinline__ void emit_body(const DecodeParams& p, const int tile_id) {
-    const Tile t = tile_of(p, tile_id);
-    const SmemMap m = smem_map(p.n_nodes, p.n_streams, p.n_slots, p.smem_data_cap, W::kRegCursors);
-    typename W::Cur q;
-    const bool map_warp = threadIdx.x < 32;
-    MapPre pre{0u, 0u, 0u, 0u, -1};
-    if (map_warp) pre = map_preload(p, t, tile_id, int(threadIdx.x));
-    const TileWindow w = stage_in<true, W>(p, t, tile_id, m, q);
-    if (map_warp) map_finish(p, t, tile_id, m, pre);
     __syncthreads();
-    wait_window(w, m);
-    if constexpr (!GENERIC) {
-        // specialised walker: staged input AND staged output only.  (!w.staged: the count pass already put the
-        // tile on the overflow list.)
-        if (!w.staged) return;
-        const uint32_t* tot = reinterpret_cast<const uint32_t*>(rv_smem + m.tot);
-        if (p.n_utf8 > 0 && tot[p.n_streams] == 0) {
-            if (threadIdx.x == 0) p.overflow_list[atomicAdd(p.overflow, 1)] = tile_id;
-            return;  // uniform
-        }
-        emit_walks<W, true>(p, t, tile_id, m, w, q);
+    const bool fast = w.staged && (flags[0] & 2u);
+    if (fast) {
+        emit_walk<W, true>(p, t, m, w, q);
+        prefetch_window(p, w);
+        if (p.n_utf8 > 0) stage_write_out(p, m);
     } else {
-        if (w.staged) emit_walks<W, true>(p, t, tile_id, m, w, q);
-        else emit_walks<W, false>(p, t, tile_id, m, w, q);
+        // the tile's bytes or its strings do not fit shared memory: walk the records in global memory and write
+        // strings straight to their Arrow buffers (slow; window sizing keeps such tiles rare)
+        if (tid == 0) atomicAdd(p.ctrl + CW_SLOW_TILES, 1ull);
+        emit_walk_global<W>(p, t, m, w, q);
     }
 }
 

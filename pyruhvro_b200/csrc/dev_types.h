@@ -34,7 +34,13 @@ enum NodeKind : uint8_t {
     NK_REC = 8,   // record (:597-616)
     NK_UNION = 9, // N-variant sparse union (:643-668)
     NK_LIST = 10, // array (:703-727)
-    NK_MAP = 11   // map (:745-770); children = [keys (NK_STR), values]
+    NK_MAP = 11,  // map (:745-770); children = [keys (NK_STR), values]
+    // wider subset (Arrow types per schema_translate.rs:58,133-143)
+    NK_BYTES = 12,     // bytes -> Binary (same wire form and buffers as NK_STR)
+    NK_FIXED = 13,     // fixed(N) -> FixedSizeBinary(N): N raw bytes, aux = N
+    NK_DEC_BYTES = 14, // decimal on bytes -> Decimal128: varint length + big-endian two's complement
+    NK_DEC_FIXED = 15, // decimal on fixed(N) -> Decimal128: N big-endian bytes, aux = N
+    NK_UUID = 16       // uuid (string logical type) -> FixedSizeBinary(16): 36-char hyphenated hex text
 };
 
 enum NodeFlags : uint8_t {
@@ -89,7 +95,19 @@ constexpr int kBlock = RV_KBLOCK;  // records per tile == threads per CTA (one r
 static_assert(kBlock % 128 == 0 && kBlock <= 1024, "tiles are whole groups of 4 warps");
 constexpr int kWarps = kBlock / 32;
 
-// Kernel parameter block (count / scan / emit).
+// Device control block of one decode call, in 64-bit words.
+enum CtrlWord : int {
+    CW_ERR = 0,         // min over (record << 8 | code); ~0 = none
+    CW_MAX_SPAN = 1,    // largest tile input span seen (bytes): sizes the shared-memory window of later calls
+    CW_MAX_UTF8 = 2,    // largest staging need of a tile seen (bytes)
+    CW_OVER = 3,        // != 0: some tile's output range exceeded the capacity the host planned (p.caps)
+    CW_SLOW_TILES = 4,  // tiles that did not fit shared memory and were walked in global memory
+    CW_IN_FIRST = 5,    // offsets[0]
+    CW_IN_LAST = 6,     // offsets[n]: the input's byte span sizes later calls' windows
+    CW_CHUNK_TOT = 8    // [k][n_streams] exact stream totals per chunk
+};
+
+// Kernel parameter block of the fused decode pass.
 struct DecodeParams {
     // input: packed Avro records (BinaryArray layout, deserialize.rs:90) with i64 offsets
     const uint8_t* data;
@@ -107,54 +125,52 @@ struct DecodeParams {
     const int32_t* sym_off;
     const uint8_t* sym_bytes;
     const int16_t* stream_slot;  // [n_streams] Utf8 data slot of a byte stream, -1 for a row stream
-    // scan scratch
-    uint32_t* tile_agg;    // [n_streams][n_tiles] per-tile totals
-    uint32_t* tile_base;   // [n_streams][n_tiles] exclusive prefix within the chunk
-    uint32_t* lane_off;    // [n_tiles][n_streams][kBlock] each record's exclusive prefix inside its tile
-    unsigned long long* chunk_tot;  // [k][n_streams]
-    unsigned long long* err;        // min over (record << 8 | code); ~0 = none
+    // scan
+    unsigned long long* tile_state;  // [n_streams][n_tiles] look-back status words {flag:2, value:62}; zero before the launch
+    unsigned long long* ctrl;        // control block (CtrlWord)
+    const uint32_t* caps;            // [k][n_streams] rows / bytes the planned buffers can take per chunk
     // output
     void* const* bufs;     // [k][n_slots]
-    // Tile routing between the two walkers.  The schema-specialised kernels only handle tiles whose
-    // bytes fit the shared-memory window; they append the others to `overflow_list` (`overflow[0]` counts them) and the generic interpreter kernels are launched over that list (tile_list != nullptr).
-    const int32_t* tile_list;  // interpreter pass over overflow tiles: blockIdx.x -> tile id
-    int32_t* overflow;         // specialised count pass: number of tiles it skipped ...
-    int32_t* overflow_list;    // ... and their ids (the specialised emit pass appends tiles whose strings do not fit
-                               // its staging area; the interpreter emit pass handles both kinds)
     int32_t n_utf8;            // Utf8 byte streams in the plan
     int32_t prefetch_dist;    // CTAs resident on the device: a CTA prefetches (into L2) the tile that far ahead
     uint32_t smem_data_cap;   // bytes of shared memory for staging a tile's input bytes
-    uint32_t smem_stage_cap;  // bytes of shared memory for staging a tile's Utf8 output bytes (emit)
+    uint32_t smem_stage_cap;  // bytes of shared memory for staging a tile's Utf8 output bytes
+    int32_t count_only;       // 1: validate + totals only (no buffers yet)
 };
 
-// Dynamic shared-memory map of count/emit CTAs (byte offsets inside the CTA's shared memory):
-//   [nodes n_nodes*32][wtot S*8*4][tot (S+1)*4][adj S*4][ptrs n_slots*8][cur S*256*4][in: data_cap][out: stage_cap]
-// alias_cur (walkers that keep their cursors in registers): the scan area `cur` overlays the input window
-// (it is only written after every lane finished reading the window) and costs no extra shared memory.
+// Readers may run a few tokens past a record's end before the deferred end-of-buffer check notices (dev_core.cuh):
+// the staged window is followed by this many readable bytes.
+constexpr uint32_t kWindowPad = 64;
+
+// Dynamic shared-memory map of a decode CTA (byte offsets inside the CTA's shared memory):
+//   [nodes n_nodes*32][ttot (S+1)*4][tbase S*4][adj S*4][flags 16][mbar 8][ptrs n_slots*8][cur S*kBlock*4][in: data_cap+pad][stage: stage_cap]
+// alias_cur (walkers that keep their cursors in registers): the scan area `cur` overlays the Utf8 staging area
+// (it is dead before the first staged byte is written) and costs no extra shared memory.
 struct SmemMap {
-    uint32_t nodes, wtot, tot, adj, mbar, ptrs, cur, in, out;
+    uint32_t nodes, ttot, tbase, adj, flags, mbar, ptrs, cur, in, stage, total;
 };
 
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-inline SmemMap smem_map(int n_nodes, int n_streams, int n_slots, uint32_t data_cap, bool alias_cur) {
+inline SmemMap smem_map(int n_nodes, int n_streams, int n_slots, uint32_t data_cap, uint32_t stage_cap, bool alias_cur) {
     SmemMap m;
     m.nodes = 0;
-    m.wtot = uint32_t(n_nodes) * 32u;
-    m.tot = m.wtot + uint32_t(n_streams) * kWarps * 4u;
-    m.adj = m.tot + uint32_t(n_streams + 1) * 4u;
-    m.mbar = (m.adj + uint32_t(n_streams) * 4u + 7u) & ~7u;  // mbarrier of the bulk-copy staging (8 bytes)
-    m.ptrs = (m.mbar + 8u + 15u) & ~15u;
+    m.ttot = uint32_t(n_nodes) * 32u;
+    m.tbase = m.ttot + uint32_t(n_streams + 1) * 4u;
+    m.adj = m.tbase + uint32_t(n_streams) * 4u;
+    m.flags = (m.adj + uint32_t(n_streams) * 4u + 15u) & ~15u;
+    m.mbar = m.flags + 16u;  // mbarrier of the bulk-copy staging (8 bytes)
+    m.ptrs = m.mbar + 16u;
     m.cur = (m.ptrs + uint32_t(n_slots) * 8u + 15u) & ~15u;
     const uint32_t cur_bytes = uint32_t(n_streams) * kBlock * 4u;
+    m.in = alias_cur ? m.cur : ((m.cur + cur_bytes + 15u) & ~15u);
+    m.stage = (m.in + data_cap + kWindowPad + 15u) & ~15u;
     if (alias_cur) {
-        m.in = m.cur;
-        const uint32_t win = data_cap > cur_bytes ? data_cap : cur_bytes;
-        m.out = (m.in + win + 15u) & ~15u;
+        m.cur = m.stage;
+        m.total = m.stage + (stage_cap > cur_bytes ? stage_cap : cur_bytes);
     } else {
-        m.in = (m.cur + cur_bytes + 15u) & ~15u;
-        m.out = (m.in + data_cap + 15u) & ~15u;
+        m.total = m.stage + stage_cap;
     }
     return m;
 }

@@ -2,15 +2,24 @@
 //
 // Replaces the L3 layer of the reference for the direct-decode path:
 //   ruhvro/src/deserialize.rs:25-30,53-121 (dispatch, clamp_chunks, build_slices, fan-out)
-// with: plan upload -> count kernel -> per-chunk scan -> exact-size Arrow arena -> emit kernel ->
-// null counts -> Arrow C Data Interface export.  One CUDA stream per call; device memory comes
-// from the stream-ordered pool, host output memory from a pinned-slab cache.
+// with: capacity-planned Arrow arena (sized from what earlier calls on the schema needed) -> ONE fused decode
+// kernel (validate, scan, look-back, emit) -> null counts -> one read-back + one stream synchronisation ->
+// Arrow C Data Interface export.  A call whose data outgrows the plan (or the first call on a schema) repeats the
+// pass once with exact sizes.  Device memory comes from a size-bucketed cache, host output memory from a
+// pinned-slab cache; the host path runs chunks on persistent worker threads bound to the GPU's NUMA node.
 #include <cuda_runtime.h>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <cstdio>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -38,7 +47,8 @@ thread_local std::string t_error;
 thread_local float t_timings[6] = {0, 0, 0, 0, 0, 0};
 thread_local int t_launches = 0;
 thread_local const char* t_walker = "none";
-thread_local long long t_overflow_tiles = 0;
+thread_local long long t_slow_tiles = 0;
+thread_local int t_passes = 0;
 
 double env_double(const char* name, double dflt) {
     const char* v = std::getenv(name);
@@ -58,6 +68,94 @@ rv_status fail(rv_status st, const std::string& msg) {
     } while (0)
 
 // ------------------------------------------------------------------------------------------
+// NUMA placement: pinned buffers and the worker threads that fill / drain them belong on the socket the GPU
+// hangs off (on the 8-GPU boxes GPUs 0-3 sit on node 0 and 4-7 on node 1; a rank whose pinned memory lives on
+// the other socket pays the inter-socket link on every PCIe transfer).  RV_NUMA=0 disables all of it.
+// ------------------------------------------------------------------------------------------
+struct NumaInfo {
+    int node = -1;
+    cpu_set_t cpus;
+    bool have_cpus = false;
+};
+
+bool numa_enabled() {
+    static const bool on = [] { const char* e = std::getenv("RV_NUMA"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+const NumaInfo& gpu_numa(int device) {
+    static std::mutex mu;
+    static std::map<int, NumaInfo> cache;
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(device);
+    if (it != cache.end()) return it->second;
+    NumaInfo info;
+    CPU_ZERO(&info.cpus);
+    char bus[64] = {0};
+    if (numa_enabled() && cudaDeviceGetPCIBusId(bus, int(sizeof bus) - 1, device) == cudaSuccess) {
+        for (char* c = bus; *c; ++c) *c = char(std::tolower(static_cast<unsigned char>(*c)));
+        const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+        if (FILE* f = std::fopen(path.c_str(), "r")) {
+            int node = -1;
+            if (std::fscanf(f, "%d", &node) == 1) info.node = node;
+            std::fclose(f);
+        }
+        if (info.node >= 0) {
+            const std::string cl = "/sys/devices/system/node/node" + std::to_string(info.node) + "/cpulist";
+            if (FILE* f = std::fopen(cl.c_str(), "r")) {
+                char buf[4096] = {0};
+                if (std::fgets(buf, sizeof buf, f)) {
+                    const char* c = buf;
+                    while (*c) {  // "0-31,64-95"
+                        char* e = nullptr;
+                        long a = std::strtol(c, &e, 10);
+                        if (e == c) break;
+                        long b = a;
+                        if (*e == '-') { c = e + 1; b = std::strtol(c, &e, 10); }
+                        for (long x = a; x <= b && x < CPU_SETSIZE; ++x) { CPU_SET(int(x), &info.cpus); info.have_cpus = true; }
+                        c = (*e == ',') ? e + 1 : e;
+                        if (*e != ',') break;
+                    }
+                }
+                std::fclose(f);
+            }
+        }
+    } else {
+        (void)cudaGetLastError();
+    }
+    return cache[device] = info;
+}
+
+// Memory policy of the calling thread: prefer `node` (-1: back to the default policy).  Failures are ignored
+// (containers may filter the syscall).
+void prefer_node(int node) {
+#if defined(SYS_set_mempolicy)
+    if (node < 0) { (void)syscall(SYS_set_mempolicy, 0 /*MPOL_DEFAULT*/, nullptr, 0UL); return; }
+    unsigned long mask[16] = {0};
+    if (node >= int(sizeof mask * 8)) return;
+    mask[node / (8 * sizeof(unsigned long))] |= 1UL << (node % (8 * sizeof(unsigned long)));
+    (void)syscall(SYS_set_mempolicy, 1 /*MPOL_PREFERRED*/, mask, (unsigned long)(sizeof mask * 8 + 1));
+#else
+    (void)node;
+#endif
+}
+
+// Worker threads: run on the GPU's socket (intersected with what the process is allowed to use) and allocate there.
+void bind_thread_to_gpu_node(int device) {
+    const NumaInfo& ni = gpu_numa(device);
+    if (ni.node < 0) return;
+    if (ni.have_cpus) {
+        cpu_set_t cur, both;
+        CPU_ZERO(&cur);
+        if (sched_getaffinity(0, sizeof cur, &cur) == 0) {
+            CPU_AND(&both, &cur, &ni.cpus);
+            if (CPU_COUNT(&both) > 0) (void)sched_setaffinity(0, sizeof both, &both);
+        }
+    }
+    prefer_node(ni.node);
+}
+
+// ------------------------------------------------------------------------------------------
 // pinned host slabs (cached: cudaHostAlloc of GiB-sized blocks costs hundreds of ms)
 // ------------------------------------------------------------------------------------------
 class PinnedCache {
@@ -75,11 +173,18 @@ class PinnedCache {
                 return p;
             }
         }
+        // fresh slabs are pinned on the socket of the calling thread's current GPU
+        int device = 0, node = -1;
+        if (cudaGetDevice(&device) == cudaSuccess) node = gpu_numa(device).node; else (void)cudaGetLastError();
+        if (node >= 0) prefer_node(node);
         void* p = nullptr;
         if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
+            (void)cudaGetLastError();
             trim(0);
-            if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+            if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); p = nullptr; }
         }
+        if (node >= 0) prefer_node(-1);
+        if (!p) return nullptr;
         *actual = want;
         return p;
     }
@@ -251,13 +356,24 @@ struct DevicePlan {
     int16_t* stream_slot = nullptr;
 };
 
-// Schema-specialised kernels (NVRTC), shared by all devices of the process.
+// Schema-specialised kernel (NVRTC) of one device: the cubin's architecture and the function attributes are
+// per device.
 struct JitState {
     bool tried = false;
     bool ok = false;
     std::string status = "not compiled";
     cudaLibrary_t lib = nullptr;
-    cudaKernel_t count = nullptr, emit = nullptr;
+    cudaKernel_t fused = nullptr;
+};
+
+// What earlier calls on this schema needed: sizes the output arena and the shared-memory windows of the next call
+// without a device round trip.
+struct SchemaStats {
+    bool valid = false;
+    std::vector<double> per_row;   // [S] stream total per record (rows of child spaces / bytes of Utf8 columns)
+    double in_per_row = 0;         // input bytes per record
+    unsigned long long max_span = 0;   // largest tile input span (bytes)
+    unsigned long long max_utf8 = 0;   // largest tile staging need (bytes)
 };
 
 struct rv_schema {
@@ -271,7 +387,8 @@ struct rv_schema {
     bool has_plan = false;
     std::mutex mu;
     std::map<int, DevicePlan> dev;  // device id -> uploaded plan
-    JitState jit;
+    std::map<int, JitState> jit;    // device id -> compiled walker
+    SchemaStats stats;
 };
 
 namespace {
@@ -298,8 +415,6 @@ rv_status device_plan(rv_schema* s, int device, DevicePlan* out) {
     return RV_OK;
 }
 
-constexpr int kOverflowGrid = 592;  // 4 CTAs per SM striding over the (normally empty) overflow list
-
 std::atomic<int> g_jit_override{-1};  // -1: follow RV_JIT; 0/1: rv_set_jit_enabled()
 
 bool jit_enabled() {
@@ -316,29 +431,31 @@ std::string device_arch(int device) {
     return "sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ((prop.major >= 9) ? "a" : "");
 }
 
-// Compiles + loads the schema-specialised kernels once per schema.  On any failure the generic
-// interpreter kernels (also on the GPU) are used and the reason is kept in jit.status.
-const JitState& ensure_jit(rv_schema* s, int device) {
-    static const JitState disabled = [] { JitState d; d.tried = true; d.status = "disabled (RV_JIT=0 / rv_set_jit_enabled(0))"; return d; }();
-    if (!jit_enabled()) return disabled;
+// Compiles + loads the schema-specialised kernel once per (schema, device).  On any failure the generic
+// interpreter kernel (also on the GPU) is used and the reason is kept in the state's status.
+JitState ensure_jit(rv_schema* s, int device) {
+    if (!jit_enabled()) { JitState d; d.tried = true; d.status = "disabled (RV_JIT=0 / rv_set_jit_enabled(0))"; return d; }
     std::lock_guard<std::mutex> g(s->mu);
-    JitState& j = s->jit;
+    JitState& j = s->jit[device];
     if (j.tried) return j;
     j.tried = true;
-    std::vector<char> cubin;
-    std::string log;
-    if (!jit_cubin(generate_kernel_source(s->plan), device_arch(device), &cubin, &log)) { j.status = "NVRTC: " + log; return j; }
-    cudaError_t e = cudaLibraryLoadData(&j.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-    if (e == cudaSuccess) e = cudaLibraryGetKernel(&j.count, j.lib, "rvj_count");
-    if (e == cudaSuccess) e = cudaLibraryGetKernel(&j.emit, j.lib, "rvj_emit");
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(reinterpret_cast<const void*>(j.count), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(reinterpret_cast<const void*>(j.emit), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    // occupancy is bounded by shared memory: ask for the largest carveout instead of the driver's guess
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(reinterpret_cast<const void*>(j.count), cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(reinterpret_cast<const void*>(j.emit), cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (e != cudaSuccess) { j.status = std::string("loading the compiled walker failed: ") + cudaGetErrorString(e); (void)cudaGetLastError(); return j; }
-    j.ok = true;
-    j.status = "ok";
+    const std::string source = generate_kernel_source(s->plan), arch = device_arch(device);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        std::vector<char> cubin;
+        std::string log;
+        if (!jit_cubin(source, arch, &cubin, &log, /*ignore_cache=*/attempt > 0)) { j.status = "NVRTC: " + log; return j; }
+        cudaError_t e = cudaLibraryLoadData(&j.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+        if (e == cudaSuccess) e = cudaLibraryGetKernel(&j.fused, j.lib, "rvj_fused");
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(reinterpret_cast<const void*>(j.fused), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        // occupancy is bounded by shared memory: ask for the largest carveout instead of the driver's guess
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(reinterpret_cast<const void*>(j.fused), cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e == cudaSuccess) { j.ok = true; j.status = "ok"; return j; }
+        // a cached cubin that does not load (corrupt file, other driver) is recompiled once, bypassing the cache
+        j.status = std::string("loading the compiled walker failed: ") + cudaGetErrorString(e);
+        (void)cudaGetLastError();
+        if (j.lib) { cudaLibraryUnload(j.lib); j.lib = nullptr; }
+        j.fused = nullptr;
+    }
     return j;
 }
 
@@ -352,12 +469,17 @@ namespace {
 struct Arena {  // one decode call's output memory; shared by the result and every exported batch
     void* dev = nullptr;
     size_t dev_actual = 0;
-    size_t bytes = 0;
+    size_t bytes = 0;        // extent of the device arena (capacity-planned layout)
     void* host = nullptr;
     size_t host_actual = 0;
+    size_t host_bytes = 0;   // extent of the host slab (exact layout)
     int device = 0;
-    ~Arena() {
+    void drop_device() {
         if (dev) devmem().put(dev, dev_actual, device);
+        dev = nullptr;
+    }
+    ~Arena() {
+        drop_device();
         if (host) pinned().put(host, host_actual);
     }
 };
@@ -387,13 +509,12 @@ const char* err_text(uint32_t code) {
     }
 }
 
-// Small pinned host block per calling thread: the template the control words are initialised from and the
-// landing zone of their read-back.  (Copies to pageable memory block the host once per copy; a decode call used
-// to make eight of them.)
+// Small pinned host block per calling thread: the template the device-side call state is initialised from and
+// the landing zone of its read-back.
 struct HostScratch {
     uint8_t* p = nullptr;
     size_t cap = 0;
-    ~HostScratch() { if (p) { cudaFreeHost(p); (void)cudaGetLastError(); } }  // worker threads of the chunk pipeline end with the call
+    ~HostScratch() { if (p) { cudaFreeHost(p); (void)cudaGetLastError(); } }
     uint8_t* get(size_t bytes) {
         if (bytes > cap) {
             if (p) cudaFreeHost(p);
@@ -424,14 +545,27 @@ struct EventPool {  // cudaEventCreate/Destroy per call is measurable at small b
 };
 thread_local EventPool t_events;
 
-// device control block of one decode call, in 64-bit words
-enum CtrlWord : int { CW_ERR = 0, CW_MAX_SPAN = 1, CW_MAX_UTF8 = 2, CW_OVERFLOW = 3, CW_OFF_FIRST = 4, CW_OFF_LAST = 5, CW_CHUNK_TOT = 8 };
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Error paths return cached device blocks (DevBuf) while work may still be queued on the stream: drain it first.
+struct SyncOnExit {
+    cudaStream_t stream;
+    bool armed = true;
+    ~SyncOnExit() { if (armed) { cudaStreamSynchronize(stream); (void)cudaGetLastError(); } }
+};
+
+// Hints of the host path, which can read the offsets: exact input bytes and the largest tile span.
+struct InputHints {
+    int64_t total_bytes = -1;
+    int64_t max_span = -1;
+};
 
 // ---- the decode call ------------------------------------------------------------------------
 rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d_offsets, int64_t n, int64_t num_chunks,
-                           int64_t total_bytes_hint, cudaStream_t stream, int device, rv_result** out, int64_t record_base = 0) {
+                           const InputHints& hints, cudaStream_t stream, int device, rv_result** out, int64_t record_base = 0) {
     const Plan& plan = s->plan;
     const int S = int(plan.streams.size());
+    const int Sx = std::max(S, 1);
     const int n_slots = int(plan.slots.size());
     // clamp_chunks (deserialize.rs:53-55)
     int64_t k64 = clamp_chunks(num_chunks, n);
@@ -447,6 +581,7 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
 
     for (int i = 0; i < 4; ++i) t_timings[i] = 0;
     t_launches = 0;
+    t_passes = 0;
     // RV_TRACE=1: host-side phase times of this call on stderr (development aid)
     static const bool trace = std::getenv("RV_TRACE") && std::getenv("RV_TRACE")[0] == '1';
     auto t_prev = std::chrono::steady_clock::now();
@@ -458,262 +593,258 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         t_prev = now;
     };
 
-    std::vector<unsigned long long> chunk_tot(size_t(k) * size_t(std::max(S, 1)), 0ull);
-    DecodeParams p{};
-    DevBuf tile_agg, tile_base, lane_off, d_ctrl, d_bufs, d_overflow;
-    DecodeParams pi{};   // interpreter pass over the tiles the specialised kernels skipped
-    size_t smem_interp = 0;
-    cudaEvent_t* ev = nullptr;
-    RV_CUDA(t_events.get(device, &ev));
-    const size_t ctrl_words = size_t(CW_CHUNK_TOT) + chunk_tot.size();
-    unsigned long long* h_ctrl = nullptr;  // pinned: [template][read-back]
-    size_t smem_count = 0, smem_emit = 0, smem_room_out = 0;
-    const size_t pad_count = size_t(env_double("RV_COUNT_SMEM_PAD", 0)), pad_emit = size_t(env_double("RV_EMIT_SMEM_PAD", 0));
-    unsigned long long max_utf8 = 0;
-    bool use_jit = false;
-    cudaKernel_t jit_count = nullptr, jit_emit = nullptr;
+    std::vector<unsigned long long> chunk_tot(size_t(k) * size_t(Sx), 0ull);
 
-    mark("setup");
-    if (n > 0) {
-        DevicePlan dp;
-        rv_status st = device_plan(s, device, &dp);
-        if (st) return st;
-        const int64_t tpc = std::max<int64_t>(1, (chunk_rows + kBlock - 1) / kBlock);
-        const int64_t tiles_last = (last_rows + kBlock - 1) / kBlock;
-        const int64_t n_tiles = tpc * (k - 1) + tiles_last;
-        if (n_tiles > 0x7FFFFFF0ll) return fail(RV_ERR_INVALID, "too many records for one call");
-
-        // tiling is known: fill it in first so the sizing kernel can use it
-        p.data = d_data; p.offsets = d_offsets; p.n = n; p.chunk_rows = chunk_rows; p.k = k;
-        p.tiles_per_chunk = int32_t(tpc); p.n_tiles = int32_t(n_tiles);
-        // control block: error word, window maxima, overflow count, input span, per-chunk stream totals —
-        // initialised by ONE copy from the pinned template and read back by one copy per phase
-        const size_t ones_words = size_t(k) * std::max<size_t>(plan.validity_slots.size(), 1);
-        h_ctrl = reinterpret_cast<unsigned long long*>(t_scratch.get((ctrl_words * 2 + ones_words) * 8));
-        if (!h_ctrl) return fail(RV_ERR_CUDA, "pinned allocation of the control block failed");
-        unsigned long long* h_back = h_ctrl + ctrl_words;
-        std::memset(h_ctrl, 0, ctrl_words * 8);
-        h_ctrl[CW_ERR] = ~0ull;
-        RV_CUDA(d_ctrl.alloc(ctrl_words * 8, stream));
-        unsigned long long* ctrl = static_cast<unsigned long long*>(d_ctrl.p);
-        RV_CUDA(cudaMemcpyAsync(ctrl, h_ctrl, ctrl_words * 8, cudaMemcpyHostToDevice, stream));
-        launch_tile_span_max(p, ctrl, stream);  // CW_MAX_SPAN, CW_OFF_FIRST, CW_OFF_LAST
-        RV_CUDA(cudaGetLastError());
-        t_launches += 1;
-        RV_CUDA(cudaMemcpyAsync(h_back, ctrl, size_t(CW_CHUNK_TOT) * 8, cudaMemcpyDeviceToHost, stream));
+    if (n == 0) {  // one empty batch; offsets buffers hold the single 0 entry
+        Layout L = compute_layout(plan, 0, k, chunk_tot.data());
+        res->chunks = std::move(L.chunks);
+        arena_sp->bytes = L.total_bytes;
+        arena_sp->dev = devmem().get(std::max<size_t>(L.total_bytes, 64), device, &arena_sp->dev_actual);
+        if (!arena_sp->dev) return fail(RV_ERR_CUDA, "device allocation of the Arrow buffer arena failed");
+        res->arenas.assign(res->chunks.size(), arena_sp);
+        RV_CUDA(cudaMemsetAsync(arena_sp->dev, 0, std::max<size_t>(L.total_bytes, 64), stream));
         RV_CUDA(cudaStreamSynchronize(stream));
-        const unsigned long long max_span = h_back[CW_MAX_SPAN];
-        int64_t total_bytes = total_bytes_hint;
-        if (total_bytes < 0) total_bytes = int64_t(h_back[CW_OFF_LAST]) - int64_t(h_back[CW_OFF_FIRST]);
-        mark("span_sync");
-        // Walker: schema-specialised (NVRTC) when available, else the generic interpreter.
-        const JitState& jit = ensure_jit(s, device);
-        use_jit = jit.ok;
-        jit_count = jit.count;
-        jit_emit = jit.emit;
-        t_walker = use_jit ? "jit" : "interp";
-        const int plan_nodes = use_jit ? 0 : int(plan.nodes.size());  // the generated walker has the plan baked in
-        // shared-memory budget: [plan +] cursors are fixed; then the tile's input bytes; then (emit) the
-        // staging area in which the tile's Utf8 output is assembled for coalesced write-out
-        const size_t fixed = smem_map(plan_nodes, S, n_slots, 0, use_jit).in;
-        const size_t limit = 227 * 1024;
-        if (fixed + 2048 > limit) return fail(RV_ERR_SCHEMA, "schema too wide for the shared-memory cursor table");
-        const double avg = total_bytes > 0 ? double(total_bytes) / double(n) : 16.0;
-        // The window is sized for the LARGEST tile (measured above), so no tile needs the interpreter overflow
-        // pass; outliers beyond 1.5x the mean tile are not allowed to shrink everyone's occupancy and do take it.
-        size_t want = std::min<size_t>(size_t(max_span), size_t(avg * kBlock * env_double("RV_IN_CLAMP", 1.5))) + 48;
-        if (use_jit) want = std::max<size_t>(want, size_t(S) * kBlock * 4);  // the scan area overlays the window
-        want = (want + 63) & ~size_t(63);
-        want = std::max<size_t>(want, 2048);
+        res->arrow_bytes = exported_bytes(plan, res->chunks);
+        *out = res.release();
+        return RV_OK;
+    }
+
+    DevicePlan dp;
+    rv_status st = device_plan(s, device, &dp);
+    if (st) return st;
+    const int64_t tpc = std::max<int64_t>(1, (chunk_rows + kBlock - 1) / kBlock);
+    const int64_t tiles_last = (last_rows + kBlock - 1) / kBlock;
+    const int64_t n_tiles = tpc * (k - 1) + tiles_last;
+    if (n_tiles > 0x7FFFFFF0ll) return fail(RV_ERR_INVALID, "too many records for one call");
+
+    // Walker: schema-specialised (NVRTC) when available, else the generic interpreter.
+    const JitState jit = ensure_jit(s, device);
+    const bool use_jit = jit.ok;
+    t_walker = use_jit ? "jit" : "interp";
+    const int plan_nodes = use_jit ? 0 : int(plan.nodes.size());  // the generated walker has the plan baked in
+
+    SchemaStats stats;
+    {
+        std::lock_guard<std::mutex> g(s->mu);
+        stats = s->stats;
+    }
+
+    DecodeParams p{};
+    p.data = d_data; p.offsets = d_offsets; p.n = n; p.chunk_rows = chunk_rows; p.k = k;
+    p.tiles_per_chunk = int32_t(tpc); p.n_tiles = int32_t(n_tiles);
+    p.nodes = dp.nodes; p.n_nodes = int32_t(plan_nodes); p.n_streams = S; p.n_slots = n_slots;
+    p.sym_off = dp.sym_off; p.sym_bytes = dp.sym_bytes; p.stream_slot = dp.stream_slot;
+    p.n_utf8 = 0;
+    for (int i = 0; i < S; ++i) p.n_utf8 += plan.streams[size_t(i)].is_rows ? 0 : 1;
+
+    // ---- shared-memory windows: [fixed tables][input window (+pad)][Utf8 staging / scan area] ----------
+    const size_t limit = 227 * 1024;
+    const size_t cur_bytes = size_t(S) * kBlock * 4;
+    const size_t fixed = smem_map(plan_nodes, S, n_slots, 0, 0, use_jit).stage;  // everything but the two windows (incl. the pad)
+    if (fixed + (use_jit ? cur_bytes : 0) + 2048 > limit) return fail(RV_ERR_SCHEMA, "schema too wide for the shared-memory cursor table");
+    size_t smem_bytes = 0;
+    auto configure = [&](const SchemaStats& st_) {  // re-evaluated per pass: a measuring pass teaches the next one
+        const double in_per_row = hints.total_bytes >= 0 ? double(hints.total_bytes) / double(n) : (st_.in_per_row > 0 ? st_.in_per_row : 128.0);
+        unsigned long long max_span = hints.max_span >= 0 ? static_cast<unsigned long long>(hints.max_span)
+                                      : (st_.max_span ? st_.max_span + st_.max_span / 16 : static_cast<unsigned long long>(in_per_row * kBlock * 1.25));
+        // The window is sized for the LARGEST tile, so that no tile takes the slow global-memory walk; outliers beyond
+        // 1.5x the mean tile are not allowed to shrink everyone's occupancy and do take it.
+        size_t want_in = std::min<size_t>(size_t(max_span), size_t(in_per_row * kBlock * env_double("RV_IN_CLAMP", 1.5))) + 48;
+        want_in = std::max<size_t>(align_up(want_in, 64), 2048);
         const size_t room = (limit - fixed - 64) & ~size_t(15);
-        size_t cap_in = std::min(want, room);
-        smem_count = smem_map(plan_nodes, S, n_slots, uint32_t(cap_in), use_jit).out;
-        smem_room_out = room > cap_in ? room - cap_in : 0;
-        p.stream_slot = dp.stream_slot;
-        const int n_nodes_param = plan_nodes;
-        p.nodes = dp.nodes; p.n_nodes = int32_t(n_nodes_param); p.n_streams = S; p.n_slots = n_slots;
-        p.sym_off = dp.sym_off; p.sym_bytes = dp.sym_bytes;
-        p.n_utf8 = 0;
-        for (int st_ = 0; st_ < S; ++st_) p.n_utf8 += plan.streams[size_t(st_)].is_rows ? 0 : 1;
+        const size_t min_stage = use_jit ? align_up(cur_bytes, 16) : 0;
+        const size_t cap_in = std::min(want_in, room - std::min(room, min_stage));
+        size_t cap_stage = 0;
+        if (p.n_utf8 > 0) {
+            // a tile's share of the Utf8 bytes: the largest seen (+6%), else everything the window could hold
+            const size_t seen = st_.max_utf8 ? size_t(st_.max_utf8 + st_.max_utf8 / 16) : cap_in + size_t(p.n_utf8) * 31;
+            double utf8_per_row = 0;
+            if (st_.valid) for (int i = 0; i < S; ++i) if (!plan.streams[size_t(i)].is_rows) utf8_per_row += st_.per_row[size_t(i)];
+            size_t want_out = seen;
+            if (st_.valid) want_out = std::min<size_t>(seen, size_t(utf8_per_row * kBlock * env_double("RV_OUT_CLAMP", 1.5)) + size_t(p.n_utf8) * 31);
+            cap_stage = align_up(want_out + 64, 64);
+            if (const char* ev_ = std::getenv("RV_NO_STAGE_OUT")) if (ev_[0] == '1') cap_stage = 0;
+        }
+        cap_stage = std::max(cap_stage, min_stage);
+        if (cap_in + cap_stage > room) cap_stage = std::max<size_t>(min_stage, (room - cap_in) & ~size_t(15));
         p.smem_data_cap = uint32_t(cap_in);
+        p.smem_stage_cap = uint32_t(cap_stage);
+        const size_t pad_smem = size_t(env_double("RV_SMEM_PAD", 0));  // development knob: occupancy sensitivity
+        smem_bytes = std::min<size_t>(smem_map(plan_nodes, S, n_slots, p.smem_data_cap, p.smem_stage_cap, use_jit).total + pad_smem, limit);
         p.prefetch_dist = 0;
         if (!(std::getenv("RV_NO_PREFETCH") && std::getenv("RV_NO_PREFETCH")[0] == '1')) {
             // CTAs resident on the device ~ how far ahead the tile a finishing CTA's successor will take is
-            const size_t per_cta = smem_count + 1024;
-            const int ctas_per_sm = int(std::max<size_t>(1, std::min<size_t>(8, (228 * 1024) / per_cta)));
+            const int ctas_per_sm = int(std::max<size_t>(1, std::min<size_t>(8, (228 * 1024) / (smem_bytes + 1024))));
             int sms = 148;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
             p.prefetch_dist = sms * ctas_per_sm;
         }
-        RV_CUDA(tile_agg.alloc(size_t(std::max(S, 1)) * size_t(n_tiles) * 4, stream));
-        RV_CUDA(tile_base.alloc(size_t(std::max(S, 1)) * size_t(n_tiles) * 4, stream));
-        RV_CUDA(lane_off.alloc(size_t(std::max(S, 1)) * size_t(n_tiles) * kBlock * 4, stream));
-        RV_CUDA(d_overflow.alloc((size_t(n_tiles) + 1) * 4, stream));
-        p.tile_agg = static_cast<uint32_t*>(tile_agg.p);
-        p.tile_base = static_cast<uint32_t*>(tile_base.p);
-        p.lane_off = static_cast<uint32_t*>(lane_off.p);
-        p.chunk_tot = ctrl + CW_CHUNK_TOT;
-        p.err = ctrl + CW_ERR;
-        p.bufs = nullptr;
+    };
 
-        mark("allocs");
-        // development knobs: extra (unused) dynamic shared memory per CTA, to measure the kernels' sensitivity to occupancy
-        smem_count = std::min<size_t>(smem_count + pad_count, limit);
+    // ---- per-call device state: [ctrl][bufs table][caps][null-count jobs][ones] in ONE block, initialised by one
+    // copy from a pinned template and (ctrl + ones) read back by one copy ------------------------------------
+    const int nv = int(plan.validity_slots.size());
+    const size_t ctrl_words = size_t(CW_CHUNK_TOT) + chunk_tot.size();
+    const size_t off_ctrl = 0;
+    const size_t off_ones = align_up(off_ctrl + ctrl_words * 8, 16);
+    const size_t ones_n = size_t(k) * size_t(std::max(nv, 1));
+    const size_t back_bytes = off_ones + ones_n * 8;               // the part that is read back
+    const size_t off_bufs = align_up(back_bytes, 16);
+    const size_t off_caps = align_up(off_bufs + size_t(k) * size_t(n_slots) * sizeof(void*), 16);
+    const size_t off_jobs = align_up(off_caps + size_t(k) * size_t(Sx) * 4, 16);
+    const size_t misc_bytes = align_up(off_jobs + size_t(k) * size_t(std::max(nv, 1)) * sizeof(NullCountJob), 16);
+    uint8_t* h_misc = t_scratch.get(misc_bytes + back_bytes);
+    if (!h_misc) return fail(RV_ERR_CUDA, "pinned allocation of the call state failed");
+    uint8_t* h_back = h_misc + misc_bytes;
+    DevBuf d_misc, d_state;
+    RV_CUDA(d_misc.alloc(misc_bytes, stream));
+    RV_CUDA(d_state.alloc(size_t(Sx) * size_t(n_tiles) * 8, stream));
+    SyncOnExit guard{stream};  // declared after the cached device blocks: runs before they go back to the cache
+    uint8_t* dm = static_cast<uint8_t*>(d_misc.p);
+    p.ctrl = reinterpret_cast<unsigned long long*>(dm + off_ctrl);
+    p.tile_state = static_cast<unsigned long long*>(d_state.p);
+    cudaEvent_t* ev = nullptr;
+    RV_CUDA(t_events.get(device, &ev));
+    mark("setup");
+
+    // chunk j's rows
+    auto rows_of = [&](int j) { return j == k - 1 ? last_rows : chunk_rows; };
+    std::vector<unsigned long long> caps(chunk_tot.size(), 0ull);
+    bool exact_caps = false;
+    if (stats.valid) {
+        const double margin = env_double("RV_CAP_MARGIN", 1.10);
+        for (int j = 0; j < k; ++j)
+            for (int i = 0; i < S; ++i) {
+                const double want = double(rows_of(j)) * stats.per_row[size_t(i)] * margin + 4096.0;
+                caps[size_t(j) * size_t(Sx) + size_t(i)] = static_cast<unsigned long long>(std::min(want, 2147483647.0));
+            }
+    }
+    bool count_only = !stats.valid;
+    Layout capL;
+    std::vector<long long> ones(ones_n, 0);
+    unsigned long long* hb_ctrl = reinterpret_cast<unsigned long long*>(h_back + off_ctrl);
+
+    for (int pass = 0; pass < 3; ++pass) {
+        ++t_passes;
+        configure(stats);
+        // ---- arena for this pass's capacities
+        uint8_t* arena = nullptr;
+        if (!count_only) {
+            capL = compute_layout(plan, n, k, caps.data());
+            arena_sp->drop_device();
+            arena_sp->bytes = capL.total_bytes;
+            arena_sp->dev = devmem().get(std::max<size_t>(capL.total_bytes, 64), device, &arena_sp->dev_actual);
+            if (!arena_sp->dev)
+                return fail(RV_ERR_CUDA, "device allocation of the Arrow buffer arena failed (" + std::to_string(capL.total_bytes) + " bytes)");
+            arena = static_cast<uint8_t*>(arena_sp->dev);
+        }
+        // ---- template of the call state
+        std::memset(h_misc, 0, misc_bytes);
+        unsigned long long* hc = reinterpret_cast<unsigned long long*>(h_misc + off_ctrl);
+        hc[CW_ERR] = ~0ull;
+        hc[CW_MAX_SPAN] = stats.max_span;   // the kernel only raises these
+        hc[CW_MAX_UTF8] = stats.max_utf8;
+        if (!count_only) {
+            void** hb = reinterpret_cast<void**>(h_misc + off_bufs);
+            for (int j = 0; j < k; ++j)
+                for (int sl = 0; sl < n_slots; ++sl) hb[size_t(j) * size_t(n_slots) + size_t(sl)] = arena + capL.chunks[size_t(j)].slot_off[size_t(sl)];
+            uint32_t* hcap = reinterpret_cast<uint32_t*>(h_misc + off_caps);
+            for (size_t i = 0; i < caps.size(); ++i) hcap[i] = uint32_t(caps[i]);
+            NullCountJob* jobs = reinterpret_cast<NullCountJob*>(h_misc + off_jobs);
+            for (int j = 0; j < k; ++j)
+                for (int v = 0; v < nv; ++v) {
+                    const int sl = plan.validity_slots[size_t(v)];
+                    const int space = plan.slots[size_t(sl)].space;
+                    NullCountJob& job = jobs[size_t(j) * size_t(nv) + size_t(v)];
+                    job.bitmap = reinterpret_cast<const uint32_t*>(arena + capL.chunks[size_t(j)].slot_off[size_t(sl)]);
+                    job.n_bits = rows_of(j);
+                    job.n_bits_dev = space == 0 ? nullptr : p.ctrl + CW_CHUNK_TOT + size_t(j) * size_t(Sx) + size_t(plan.space_stream[size_t(space)]);
+                }
+        }
+        p.bufs = count_only ? nullptr : reinterpret_cast<void* const*>(dm + off_bufs);
+        p.caps = count_only ? nullptr : reinterpret_cast<const uint32_t*>(dm + off_caps);
+        p.count_only = count_only ? 1 : 0;
+
+        RV_CUDA(cudaMemcpyAsync(dm, h_misc, misc_bytes, cudaMemcpyHostToDevice, stream));
+        RV_CUDA(cudaMemsetAsync(d_state.p, 0, size_t(Sx) * size_t(n_tiles) * 8, stream));
+        if (!count_only && capL.zero_bytes) RV_CUDA(cudaMemsetAsync(arena, 0, capL.zero_bytes, stream));
         RV_CUDA(cudaEventRecord(ev[0], stream));
-        p.tile_list = nullptr;
-        p.overflow = reinterpret_cast<int32_t*>(ctrl + CW_OVERFLOW);
-        p.overflow_list = static_cast<int32_t*>(d_overflow.p);
         if (use_jit) {
             void* args[] = {&p};
-            RV_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(jit_count), dim3(unsigned(p.n_tiles)), dim3(kBlock), args, smem_count, stream));
-            pi = p;
-            pi.n_nodes = int32_t(plan.nodes.size());
-            pi.tile_list = static_cast<const int32_t*>(d_overflow.p);
-            pi.smem_stage_cap = 0;
-            pi.smem_data_cap = uint32_t(std::min<size_t>(cap_in, (limit - smem_map(pi.n_nodes, S, n_slots, 0, false).in - 64) & ~size_t(15)));
-            smem_interp = smem_map(pi.n_nodes, S, n_slots, pi.smem_data_cap, false).out;
-            launch_count(pi, kOverflowGrid, smem_interp, stream);
-            t_launches += 1;
+            RV_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(jit.fused), dim3(unsigned(p.n_tiles)), dim3(kBlock), args, smem_bytes, stream));
         } else {
-            launch_count(p, p.n_tiles, smem_count, stream);
+            launch_fused(p, smem_bytes, stream);
         }
         RV_CUDA(cudaEventRecord(ev[1], stream));
-        launch_scan(p, stream);
-        RV_CUDA(cudaEventRecord(ev[2], stream));
-        launch_tile_utf8_max(p, ctrl + CW_MAX_UTF8, stream);
         t_launches += 1;
+        if (!count_only && nv > 0) {
+            launch_null_count(reinterpret_cast<const NullCountJob*>(dm + off_jobs), k * nv, reinterpret_cast<long long*>(dm + off_ones), stream);
+            t_launches += 1;
+        }
+        RV_CUDA(cudaEventRecord(ev[2], stream));
         RV_CUDA(cudaGetLastError());
-        t_launches += S > 0 ? 2 : 1;
-
-        RV_CUDA(cudaMemcpyAsync(h_back, ctrl, ctrl_words * 8, cudaMemcpyDeviceToHost, stream));
-        mark("count_launched");
+        RV_CUDA(cudaMemcpyAsync(h_back, dm, back_bytes, cudaMemcpyDeviceToHost, stream));
+        mark("launched");
         RV_CUDA(cudaStreamSynchronize(stream));
-        mark("count_sync");
-        const unsigned long long err_word = h_back[CW_ERR];
-        const int overflow_n = int(uint32_t(h_back[CW_OVERFLOW]));
-        max_utf8 = h_back[CW_MAX_UTF8];
-        std::memcpy(chunk_tot.data(), h_back + CW_CHUNK_TOT, chunk_tot.size() * 8);
-        t_overflow_tiles = overflow_n;
+        mark("sync");
+
+        const unsigned long long err_word = hb_ctrl[CW_ERR];
         if (err_word != ~0ull) {
             const uint32_t code = uint32_t(err_word & 0xFF);
             return fail(rv_status(code), std::string(err_text(code)) + " (record " + std::to_string(int64_t(err_word >> 8) + record_base) + ")");
         }
-    }
-
-    // ---- exact arena layout -------------------------------------------------------------
-    Layout L = compute_layout(plan, n, k, chunk_tot.data());
-    res->chunks = std::move(L.chunks);
-    const size_t zero_bytes = L.zero_bytes, total = L.total_bytes;
-    arena_sp->bytes = total;
-    arena_sp->dev = devmem().get(std::max<size_t>(total, 64), device, &arena_sp->dev_actual);
-    if (!arena_sp->dev) return fail(RV_ERR_CUDA, "device allocation of the Arrow buffer arena failed (" + std::to_string(total) + " bytes)");
-    uint8_t* arena = static_cast<uint8_t*>(arena_sp->dev);
-    res->arenas.assign(res->chunks.size(), arena_sp);
-
-    if (n > 0) {
-        if (zero_bytes) RV_CUDA(cudaMemsetAsync(arena, 0, zero_bytes, stream));
-        // pointer table
-        std::vector<void*> h_bufs(size_t(k) * size_t(n_slots));
-        for (int j = 0; j < k; ++j)
-            for (int sl = 0; sl < n_slots; ++sl) h_bufs[size_t(j) * size_t(n_slots) + size_t(sl)] = arena + res->chunks[size_t(j)].slot_off[size_t(sl)];
-        RV_CUDA(d_bufs.alloc(h_bufs.size() * sizeof(void*), stream));
-        RV_CUDA(cudaMemcpyAsync(d_bufs.p, h_bufs.data(), h_bufs.size() * sizeof(void*), cudaMemcpyHostToDevice, stream));
-        p.bufs = static_cast<void* const*>(d_bufs.p);
-
-        // Utf8 staging area of the emit CTAs, sized from the now-known string totals: a tile's share of
-        // every Utf8 column (+12%) plus 16 bytes of alignment slack per column.
+        std::memcpy(chunk_tot.data(), hb_ctrl + CW_CHUNK_TOT, chunk_tot.size() * 8);
+        const bool over = hb_ctrl[CW_OVER] != 0ull;
+        t_slow_tiles = (long long)hb_ctrl[CW_SLOW_TILES];
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev[0], ev[1]);
+        // ---- remember what this call needed
         {
-            unsigned long long utf8 = 0;
-            int n_utf8 = 0;
-            for (int st_ = 0; st_ < S; ++st_) {
-                if (plan.streams[size_t(st_)].is_rows) continue;
-                ++n_utf8;
-                for (int j = 0; j < k; ++j) utf8 += chunk_tot[size_t(j) * size_t(S) + size_t(st_)];
+            std::lock_guard<std::mutex> g(s->mu);
+            SchemaStats& ss = s->stats;
+            if (ss.per_row.size() != size_t(S)) ss.per_row.assign(size_t(S), 0.0);
+            for (int i = 0; i < S; ++i) {
+                double worst = 0;  // the densest chunk decides: every chunk's buffers must hold
+                for (int j = 0; j < k; ++j) worst = std::max(worst, double(chunk_tot[size_t(j) * size_t(Sx) + size_t(i)]) / double(std::max<int64_t>(rows_of(j), 1)));
+                double& r = ss.per_row[size_t(i)];
+                r = (!ss.valid || worst > r) ? worst : r * 0.9 + worst * 0.1;
             }
-            size_t cap_out = 0;
-            if (n_utf8 > 0) {
-                const double per_tile = double(utf8) / double(p.n_tiles);
-                // the largest tile's Utf8 bytes (measured), clamped at 1.5x the mean for outliers: a tile that
-                // outgrows the staging area writes its strings straight to global memory
-                cap_out = std::min<size_t>(size_t(max_utf8), size_t(per_tile * env_double("RV_OUT_CLAMP", 1.5)) + size_t(n_utf8) * 31) + 64;
-                cap_out = (cap_out + 63) & ~size_t(63);
-                if (cap_out > smem_room_out) cap_out = smem_room_out & ~size_t(15);
-                if (cap_out < 256) cap_out = 0;  // no room at all: strings go straight to global (interpreter pass)
-            }
-            if (const char* ev_ = std::getenv("RV_NO_STAGE_OUT")) if (ev_[0] == '1') cap_out = 0;
-            p.smem_stage_cap = uint32_t(cap_out);
-            smem_emit = std::min<size_t>(smem_count - pad_count + cap_out + pad_emit, 227 * 1024);
-            if (p.prefetch_dist > 0) {
-                int sms = 148;
-                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-                p.prefetch_dist = sms * int(std::max<size_t>(1, std::min<size_t>(8, (228 * 1024) / (smem_emit + 1024))));
-            }
+            if (hints.total_bytes >= 0) ss.in_per_row = double(hints.total_bytes) / double(n);
+            else if (hb_ctrl[CW_IN_LAST] >= hb_ctrl[CW_IN_FIRST]) ss.in_per_row = double(hb_ctrl[CW_IN_LAST] - hb_ctrl[CW_IN_FIRST]) / double(n);
+            ss.max_span = std::max(ss.max_span, hb_ctrl[CW_MAX_SPAN]);
+            ss.max_utf8 = std::max(ss.max_utf8, hb_ctrl[CW_MAX_UTF8]);
+            ss.valid = true;
+            stats = ss;
         }
-        mark("layout");
-        RV_CUDA(cudaEventRecord(ev[3], stream));
-        if (use_jit) {
-            void* args[] = {&p};
-            RV_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(jit_emit), dim3(unsigned(p.n_tiles)), dim3(kBlock), args, smem_emit, stream));
-            pi.bufs = p.bufs;
-            launch_emit(pi, kOverflowGrid, smem_interp, stream);
-            t_launches += 1;
-        } else {
-            launch_emit(p, p.n_tiles, smem_emit, stream);
+        if (!count_only && !over) {
+            t_timings[0] = ms;
+            cudaEventElapsedTime(&t_timings[3], ev[1], ev[2]);
+            std::memcpy(ones.data(), h_back + off_ones, ones_n * 8);
+            break;
         }
-        RV_CUDA(cudaEventRecord(ev[4], stream));
-        RV_CUDA(cudaGetLastError());
-        t_launches += 1;
-
-        // null counts of every validity bitmap
-        const int nv = int(plan.validity_slots.size());
-        std::vector<long long> ones(size_t(k) * size_t(std::max(nv, 1)), 0);
-        DevBuf d_jobs, d_ones;
-        if (nv > 0) {
-            std::vector<NullCountJob> jobs(size_t(k) * size_t(nv));
-            for (int j = 0; j < k; ++j)
-                for (int v = 0; v < nv; ++v) {
-                    const int sl = plan.validity_slots[size_t(v)];
-                    const ChunkOut& c = res->chunks[size_t(j)];
-                    jobs[size_t(j) * size_t(nv) + size_t(v)] =
-                        NullCountJob{reinterpret_cast<const uint32_t*>(arena + c.slot_off[size_t(sl)]), c.space_rows[size_t(plan.slots[size_t(sl)].space)]};
-                }
-            RV_CUDA(d_jobs.alloc(jobs.size() * sizeof(NullCountJob), stream));
-            RV_CUDA(d_ones.alloc(ones.size() * 8, stream));
-            RV_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(NullCountJob), cudaMemcpyHostToDevice, stream));
-            RV_CUDA(cudaMemsetAsync(d_ones.p, 0, ones.size() * 8, stream));
-            launch_null_count(static_cast<const NullCountJob*>(d_jobs.p), int(jobs.size()), static_cast<long long*>(d_ones.p), stream);
-            RV_CUDA(cudaGetLastError());
-            t_launches += 1;
-            RV_CUDA(cudaEventRecord(ev[5], stream));
-            RV_CUDA(cudaMemcpyAsync(h_ctrl + ctrl_words * 2, d_ones.p, ones.size() * 8, cudaMemcpyDeviceToHost, stream));
-        } else {
-            RV_CUDA(cudaEventRecord(ev[5], stream));
-        }
-        // the overflow counter again: the specialised emit pass may have added tiles whose strings did not fit
-        if (use_jit) RV_CUDA(cudaMemcpyAsync(h_ctrl + ctrl_words, d_ctrl.p ? static_cast<unsigned long long*>(d_ctrl.p) + CW_OVERFLOW : nullptr, 8, cudaMemcpyDeviceToHost, stream));
-        mark("emit_launched");
-        RV_CUDA(cudaStreamSynchronize(stream));
-        mark("emit_sync");
-        if (use_jit) t_overflow_tiles = int(uint32_t(h_ctrl[ctrl_words]));
-        if (nv > 0) std::memcpy(ones.data(), h_ctrl + ctrl_words * 2, ones.size() * 8);
-        for (int j = 0; j < k; ++j)
-            for (int v = 0; v < nv; ++v) {
-                const int sl = plan.validity_slots[size_t(v)];
-                ChunkOut& c = res->chunks[size_t(j)];
-                c.null_count[size_t(sl)] = c.space_rows[size_t(plan.slots[size_t(sl)].space)] - ones[size_t(j) * size_t(nv) + size_t(v)];
-            }
-        cudaEventElapsedTime(&t_timings[0], ev[0], ev[1]);
-        cudaEventElapsedTime(&t_timings[1], ev[1], ev[2]);
-        cudaEventElapsedTime(&t_timings[2], ev[3], ev[4]);
-        cudaEventElapsedTime(&t_timings[3], ev[4], ev[5]);
-    } else {
-        // n == 0: one empty batch; offsets buffers hold the single 0 entry
-        RV_CUDA(cudaMemsetAsync(arena, 0, std::max<size_t>(total, 64), stream));
-        RV_CUDA(cudaStreamSynchronize(stream));
+        // the pass only measured (first call on the schema, or the data outgrew the plan): repeat with exact sizes
+        t_timings[1] += ms;
+        if (exact_caps) return fail(RV_ERR_CUDA, "internal error: exact-size pass reported a capacity overflow");
+        caps = chunk_tot;
+        exact_caps = true;
+        count_only = false;
     }
+
+    // ---- exact logical sizes on top of the capacity-planned placement ---------------------------
+    Layout L = compute_layout(plan, n, k, chunk_tot.data());
+    for (int j = 0; j < k; ++j) L.chunks[size_t(j)].slot_off = capL.chunks[size_t(j)].slot_off;
+    res->chunks = std::move(L.chunks);
+    res->arenas.assign(res->chunks.size(), arena_sp);
+    for (int j = 0; j < k; ++j)
+        for (int v = 0; v < nv; ++v) {
+            const int sl = plan.validity_slots[size_t(v)];
+            ChunkOut& c = res->chunks[size_t(j)];
+            c.null_count[size_t(sl)] = c.space_rows[size_t(plan.slots[size_t(sl)].space)] - ones[size_t(j) * size_t(nv) + size_t(v)];
+        }
     res->arrow_bytes = exported_bytes(plan, res->chunks);
     mark("finish");
-    if (trace) std::fprintf(stderr, "[rv trace] %s\n", trace_line.c_str());
+    if (trace) std::fprintf(stderr, "[rv trace] passes=%d %s\n", t_passes, trace_line.c_str());
+    guard.armed = false;  // the last pass synchronised the stream
     *out = res.release();
     return RV_OK;
 }
@@ -777,7 +908,9 @@ void rv_schema_release(rv_schema* s) {
             cudaFree(kv.second.sym_bytes);
             cudaFree(kv.second.stream_slot);
         }
-        if (s->jit.lib) cudaLibraryUnload(s->jit.lib);
+        for (auto& kv : s->jit)
+            if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
+        (void)cudaGetLastError();
         delete s;
     }
 }
@@ -806,41 +939,88 @@ rv_status rv_decode_device(const rv_schema* s, const uint8_t* d_data, const int6
     int device = 0;
     st = ensure_cuda(&device);
     if (st) return st;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     try {
-        return decode_on_device(const_cast<rv_schema*>(s), d_data, d_offsets, n, num_chunks, -1, static_cast<cudaStream_t>(cuda_stream), device, out);
+        st = decode_on_device(const_cast<rv_schema*>(s), d_data, d_offsets, n, num_chunks, InputHints{}, stream, device, out);
     } catch (const std::exception& e) {
-        return fail(RV_ERR_INVALID, e.what());
+        st = fail(RV_ERR_INVALID, e.what());
     }
+    // error paths hand cached device blocks back: nothing may still be running on them
+    if (st) { const std::string keep = t_error; cudaStreamSynchronize(stream); (void)cudaGetLastError(); t_error = keep; }
+    return st;
 }
 
 }  // extern "C"
 
 namespace {
 
-// Copies one arena to a pinned host slab on `stream` (synchronises the stream).
-rv_status arena_to_host(Arena& a, cudaStream_t stream, float* ms) {
+// Brings one arena to a pinned host slab on `stream`: the capacity-planned device arena is packed into an
+// exact-size one (device -> device, compact_kernel), that one is copied down, and BOTH device blocks go back to the
+// cache — a host batch keeps only its pinned slab alive.  Rewrites the chunks' slot offsets to the exact layout.
+rv_status arena_to_host(rv_result& r, Arena& a, cudaStream_t stream, float* ms) {
     if (a.host) return RV_OK;
+    const Plan& plan = r.schema->plan;
+    const int n_slots = int(plan.slots.size());
+    // exact layout over the chunks this arena backs
+    std::vector<size_t> mine;
+    for (size_t i = 0; i < r.chunks.size(); ++i)
+        if (r.arenas[i].get() == &a) mine.push_back(i);
+    size_t total = 0;
+    std::vector<CompactJob> jobs;
+    std::vector<std::vector<size_t>> new_off(mine.size(), std::vector<size_t>(size_t(n_slots), 0));
+    const uint8_t* src = static_cast<const uint8_t*>(a.dev);
+    for (int pass = 0; pass < 2; ++pass)  // same order as compute_layout: zero-initialised bit buffers first
+        for (size_t mi = 0; mi < mine.size(); ++mi) {
+            const ChunkOut& c = r.chunks[mine[mi]];
+            for (int sl = 0; sl < n_slots; ++sl) {
+                const Slot& slot = plan.slots[size_t(sl)];
+                if (slot.zero_init != (pass == 0)) continue;
+                size_t bytes = size_t(c.slot_bytes[size_t(sl)]);
+                if (slot.role == SlotRole::Validity || slot.role == SlotRole::Bits) bytes = size_t((c.space_rows[size_t(slot.space)] + 31) / 32) * 4;
+                new_off[mi][size_t(sl)] = total;
+                if (bytes) jobs.push_back(CompactJob{src + c.slot_off[size_t(sl)], reinterpret_cast<uint8_t*>(total), int64_t(bytes)});  // dst: offset for now
+                total += (std::max<size_t>(bytes, 1) + 63) & ~size_t(63);
+            }
+        }
+    const size_t host_bytes = std::max<size_t>(total, 64);
     size_t actual = 0;
-    void* h = pinned().get(std::max<size_t>(a.bytes, 64), &actual);
+    void* h = pinned().get(host_bytes, &actual);
     if (!h) return fail(RV_ERR_CUDA, "pinned host allocation failed");
-    cudaEvent_t e0, e1;
-    RV_CUDA(cudaEventCreate(&e0));
-    RV_CUDA(cudaEventCreate(&e1));
-    cudaEventRecord(e0, stream);
-    cudaError_t e = cudaMemcpyAsync(h, a.dev, a.bytes, cudaMemcpyDeviceToHost, stream);
-    cudaEventRecord(e1, stream);
+    DevBuf packed, d_jobs;
+    cudaError_t e = packed.alloc(host_bytes, stream);
+    if (e == cudaSuccess) e = d_jobs.alloc(std::max<size_t>(jobs.size(), 1) * sizeof(CompactJob), stream);
+    uint8_t* h_jobs = t_scratch.get(std::max<size_t>(jobs.size(), 1) * sizeof(CompactJob));
+    if (e != cudaSuccess || !h_jobs) { pinned().put(h, actual); return fail(RV_ERR_CUDA, "device allocation for the host export failed"); }
+    SyncOnExit guard{stream};
+    for (CompactJob& job : jobs) job.dst = static_cast<uint8_t*>(packed.p) + reinterpret_cast<size_t>(job.dst);
+    std::memcpy(h_jobs, jobs.data(), jobs.size() * sizeof(CompactJob));
+    cudaEvent_t* ev = nullptr;
+    e = t_events.get(a.device, &ev);
+    if (e == cudaSuccess && !jobs.empty()) e = cudaMemcpyAsync(d_jobs.p, h_jobs, jobs.size() * sizeof(CompactJob), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess && !jobs.empty()) {
+        const int parts = int(std::max<size_t>(1, std::min<size_t>(64, (total / std::max<size_t>(jobs.size(), 1)) >> 16)));
+        launch_compact(static_cast<const CompactJob*>(d_jobs.p), int(jobs.size()), parts, stream);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(ev[6], stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, packed.p, host_bytes, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ev[7], stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    float t = 0;
-    cudaEventElapsedTime(&t, e0, e1);
-    if (ms) *ms += t;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (e != cudaSuccess) {
+        (void)cudaStreamSynchronize(stream);
+        (void)cudaGetLastError();
         pinned().put(h, actual);
         return fail(RV_ERR_CUDA, std::string("device->host copy: ") + cudaGetErrorString(e));
     }
+    float t = 0;
+    cudaEventElapsedTime(&t, ev[6], ev[7]);
+    if (ms) *ms += t;
+    guard.armed = false;
     a.host = h;
     a.host_actual = actual;
+    a.host_bytes = host_bytes;
+    a.drop_device();
+    for (size_t mi = 0; mi < mine.size(); ++mi) r.chunks[mine[mi]].slot_off = new_off[mi];
     return RV_OK;
 }
 
@@ -849,40 +1029,51 @@ rv_status decode_host_range(rv_schema* s, const uint8_t* data, const int64_t* of
                             cudaStream_t stream, int device, rv_result** out, float* h2d_ms, float* d2h_ms) {
     const int64_t n = r1 - r0;
     DevBuf d_data, d_off;
-    int64_t total = 0;
+    InputHints hints;
     const uint8_t* base = nullptr;
+    rv_status st = RV_OK;
     if (n > 0) {
         const int64_t b0 = offsets[r0];
-        total = offsets[r1] - b0;
+        const int64_t total = offsets[r1] - b0;
         if (total < 0) return fail(RV_ERR_INVALID, "offsets are not monotonic");
+        hints.total_bytes = total;
+        // the largest tile span, exactly (the host can read the offsets): sizes the shared-memory window
+        {
+            const int64_t k = clamp_chunks(num_chunks, n);
+            const int64_t cr = n / k;
+            int64_t mx = 0;
+            for (int64_t j = 0; j < k; ++j) {
+                const int64_t cs = r0 + j * cr, ce = (j == k - 1) ? r1 : cs + cr;
+                for (int64_t a = cs; a < ce; a += kBlock) mx = std::max(mx, offsets[std::min(a + kBlock, ce)] - offsets[a]);
+            }
+            hints.max_span = mx;
+        }
         RV_CUDA(d_data.alloc(size_t(total) + 64, stream));
         RV_CUDA(d_off.alloc(size_t(n + 1) * 8, stream));
-        cudaEvent_t e0, e1;
-        RV_CUDA(cudaEventCreate(&e0));
-        RV_CUDA(cudaEventCreate(&e1));
-        cudaEventRecord(e0, stream);
+        cudaEvent_t* ev = nullptr;
+        RV_CUDA(t_events.get(device, &ev));
+        cudaEventRecord(ev[4], stream);
         // The device copy keeps the caller's absolute offsets: the base pointer is biased so that
         // base + offsets[i] addresses record i (kept 16-byte aligned by the b0 & 15 shift).
         cudaError_t e = cudaMemcpyAsync(static_cast<uint8_t*>(d_data.p) + (b0 & 15), data + b0, size_t(total), cudaMemcpyHostToDevice, stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_off.p, offsets + r0, size_t(n + 1) * 8, cudaMemcpyHostToDevice, stream);
-        cudaEventRecord(e1, stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        float t = 0;
-        cudaEventElapsedTime(&t, e0, e1);
-        if (h2d_ms) *h2d_ms += t;
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
-        if (e != cudaSuccess) return fail(RV_ERR_CUDA, std::string("host->device copy: ") + cudaGetErrorString(e));
+        cudaEventRecord(ev[5], stream);
+        if (e != cudaSuccess) { (void)cudaStreamSynchronize(stream); return fail(RV_ERR_CUDA, std::string("host->device copy: ") + cudaGetErrorString(e)); }
         base = static_cast<const uint8_t*>(d_data.p) + (b0 & 15) - b0;
     }
-    rv_status st;
     try {
-        st = decode_on_device(s, base, static_cast<const int64_t*>(d_off.p), n, num_chunks, total, stream, device, out, r0);
+        st = decode_on_device(s, base, static_cast<const int64_t*>(d_off.p), n, num_chunks, hints, stream, device, out, r0);
     } catch (const std::exception& e) {
-        return fail(RV_ERR_INVALID, e.what());
+        st = fail(RV_ERR_INVALID, e.what());
     }
-    if (st) return st;
-    st = arena_to_host(*(*out)->arenas[0], stream, d2h_ms);
+    if (st) { const std::string keep = t_error; cudaStreamSynchronize(stream); (void)cudaGetLastError(); t_error = keep; return st; }
+    if (n > 0 && h2d_ms) {
+        cudaEvent_t* ev = nullptr;
+        float t = 0;
+        if (t_events.get(device, &ev) == cudaSuccess && cudaEventElapsedTime(&t, ev[4], ev[5]) == cudaSuccess) *h2d_ms += t;
+        (void)cudaGetLastError();
+    }
+    st = arena_to_host(**out, *(*out)->arenas[0], stream, d2h_ms);
     if (st) { rv_result_free(*out); *out = nullptr; }
     return st;
 }
@@ -890,6 +1081,59 @@ rv_status decode_host_range(rv_schema* s, const uint8_t* data, const int64_t* of
 bool pipeline_enabled() {
     const char* e = std::getenv("RV_PIPELINE");
     return !(e && e[0] == '0');
+}
+
+// ---- persistent chunk workers ---------------------------------------------------------------------
+// The host path decodes the chunks of a call (independent batches) on a few long-lived threads per device, each
+// with its own stream, events and pinned scratch, so that the H2D copy of chunk i+1 overlaps the kernels and the
+// D2H copy of chunk i.  (Spawning threads per call re-created all of that every time.)
+class WorkerPool {
+  public:
+    explicit WorkerPool(int device, int n) : device_(device) {
+        for (int w = 0; w < n; ++w) std::thread([this, w] { run(w); }).detach();
+    }
+    void submit(std::function<void(cudaStream_t)> fn) {
+        { std::lock_guard<std::mutex> g(mu_); q_.push_back(std::move(fn)); }
+        cv_.notify_one();
+    }
+
+  private:
+    void run(int w) {
+        cudaSetDevice(device_);
+        bind_thread_to_gpu_node(device_);
+        cudaStream_t stream = worker_stream(device_, w);
+        for (;;) {
+            std::function<void(cudaStream_t)> fn;
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                cv_.wait(g, [&] { return !q_.empty(); });
+                fn = std::move(q_.front());
+                q_.pop_front();
+            }
+            fn(stream);
+        }
+    }
+    int device_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::function<void(cudaStream_t)>> q_;
+};
+
+int worker_count() {
+    int want = 4;
+    if (const char* ev = std::getenv("RV_WORKERS")) want = std::max(1, std::atoi(ev));
+    return std::min(want, 16);
+}
+
+WorkerPool& worker_pool(int device) {
+    static std::mutex mu;
+    static std::map<int, WorkerPool*> pools;  // intentionally leaked: the threads live until the process ends
+    std::lock_guard<std::mutex> g(mu);
+    auto it = pools.find(device);
+    if (it != pools.end()) return *it->second;
+    WorkerPool* p = new WorkerPool(device, worker_count());
+    pools[device] = p;
+    return *p;
 }
 
 }  // namespace
@@ -900,7 +1144,7 @@ rv_status rv_result_to_host(rv_result* r) {
     if (!r) return fail(RV_ERR_INVALID, "null result");
     float ms = 0;
     for (auto& a : r->arenas) {
-        rv_status st = arena_to_host(*a, nullptr, &ms);
+        rv_status st = arena_to_host(*r, *a, nullptr, &ms);
         if (st) return st;
     }
     t_timings[5] = ms;
@@ -921,55 +1165,62 @@ rv_status rv_decode_host(const rv_schema* s_, const uint8_t* data, const int64_t
     const int64_t k = clamp_chunks(num_chunks, n);
     float h2d = 0, d2h = 0;
     // pipelining pays when every chunk is big enough to amortise its own launches and copies; many small
-    // chunks go through ONE launch set that handles all chunks at once
+    // chunks go through ONE launch that handles all chunks at once
     if (k < 2 || n / k < 16384 || !pipeline_enabled()) {
         st = decode_host_range(s, data, offsets, 0, n, num_chunks, nullptr, device, out, &h2d, &d2h);
         t_timings[4] = h2d;
         t_timings[5] = d2h;
         return st;
     }
-    // Chunks are independent batches (deserialize.rs:57-68,92-119): decode them on a few worker streams so
-    // the H2D copy of chunk i+1 overlaps the kernels and the D2H copy of chunk i (full-duplex PCIe).  This
-    // is the GPU-side analogue of the reference fanning chunks out to its thread pool.
+    // Chunks are independent batches (deserialize.rs:57-68,92-119): the GPU-side analogue of the reference fanning
+    // chunks out to its thread pool.
     const int64_t chunk_rows = n / k;
+    struct Call {
+        std::mutex mu;
+        std::condition_variable cv;
+        int64_t left;
+        float acc[6] = {0, 0, 0, 0, 0, 0};
+        int launches = 0, passes = 0;
+        long long slow = 0;
+        const char* walker = "none";
+    } call;
+    call.left = k;
     std::vector<rv_result*> parts(size_t(k), nullptr);
     std::vector<rv_status> status(size_t(k), RV_OK);
     std::vector<std::string> message{size_t(k), std::string()};
-    std::atomic<int64_t> next{0};
-    std::mutex acc_mu;
-    float acc[6] = {0, 0, 0, 0, 0, 0};
-    int acc_launches = 0;
-    long long acc_overflow = 0;
-    const char* walker = "none";
-    auto worker = [&](int wid) {
-        cudaSetDevice(device);
-        cudaStream_t stream = worker_stream(device, wid);
-        for (;;) {
-            const int64_t i = next.fetch_add(1);
-            if (i >= k) break;
+    WorkerPool& pool = worker_pool(device);
+    for (int64_t i = 0; i < k; ++i) {
+        pool.submit([&, i](cudaStream_t stream) {
             const int64_t r0 = i * chunk_rows, r1 = (i == k - 1) ? n : r0 + chunk_rows;
             float hm = 0, dm = 0;
-            status[size_t(i)] = decode_host_range(s, data, offsets, r0, r1, 1, stream, device, &parts[size_t(i)], &hm, &dm);
-            if (status[size_t(i)]) message[size_t(i)] = t_error;
-            std::lock_guard<std::mutex> g(acc_mu);
-            for (int q = 0; q < 4; ++q) acc[q] += t_timings[q];
-            acc[4] += hm;
-            acc[5] += dm;
-            acc_launches += t_launches;
-            acc_overflow += t_overflow_tiles;
-            walker = t_walker;
-        }
-    };
-    int want_workers = 4;
-    if (const char* ev = std::getenv("RV_WORKERS")) want_workers = std::max(1, std::atoi(ev));
-    const int n_workers = int(std::min<int64_t>(k, want_workers));
-    std::vector<std::thread> threads;
-    for (int w = 0; w < n_workers; ++w) threads.emplace_back(worker, w);
-    for (auto& t : threads) t.join();
-    for (int q = 0; q < 6; ++q) t_timings[q] = acc[q];
-    t_launches = acc_launches;
-    t_overflow_tiles = acc_overflow;
-    t_walker = walker;
+            rv_status rc;
+            try {
+                rc = decode_host_range(s, data, offsets, r0, r1, 1, stream, device, &parts[size_t(i)], &hm, &dm);
+            } catch (const std::exception& e) {
+                rc = fail(RV_ERR_INVALID, e.what());
+            }
+            status[size_t(i)] = rc;
+            if (rc) message[size_t(i)] = t_error;
+            std::lock_guard<std::mutex> g(call.mu);
+            for (int q = 0; q < 4; ++q) call.acc[q] += t_timings[q];
+            call.acc[4] += hm;
+            call.acc[5] += dm;
+            call.launches += t_launches;
+            call.passes = std::max(call.passes, t_passes);
+            call.slow += t_slow_tiles;
+            call.walker = t_walker;
+            if (--call.left == 0) call.cv.notify_all();
+        });
+    }
+    {
+        std::unique_lock<std::mutex> g(call.mu);
+        call.cv.wait(g, [&] { return call.left == 0; });
+    }
+    for (int q = 0; q < 6; ++q) t_timings[q] = call.acc[q];
+    t_launches = call.launches;
+    t_passes = call.passes;
+    t_slow_tiles = call.slow;
+    t_walker = call.walker;
     auto res = std::make_unique<rv_result>();
     res->schema = rv_schema_retain(s);
     rv_status first = RV_OK;
@@ -1002,7 +1253,7 @@ int64_t rv_result_buffer_bytes(const rv_result* r) {
     int64_t total = 0;
     const Arena* last = nullptr;
     for (auto& a : r->arenas) {
-        if (a.get() != last) total += int64_t(a->bytes);
+        if (a.get() != last) total += int64_t(a->host ? a->host_bytes : a->bytes);
         last = a.get();
     }
     return total;
@@ -1023,6 +1274,7 @@ rv_status rv_result_export(rv_result* r, int64_t batch, struct ArrowArray* out_a
 rv_status rv_result_export_device(rv_result* r, int64_t batch, struct ArrowDeviceArray* out_array, struct ArrowSchema* out_schema) {
     if (!r || !out_array) return fail(RV_ERR_INVALID, "null argument");
     if (batch < 0 || batch >= int64_t(r->chunks.size())) return fail(RV_ERR_INVALID, "batch index out of range");
+    if (!r->arenas[size_t(batch)]->dev) return fail(RV_ERR_INVALID, "result was moved to host memory: use rv_result_export()");
     if (out_schema) {
         rv_status st = rv_schema_export_arrow(r->schema, out_schema);
         if (st) return st;
@@ -1067,6 +1319,7 @@ int rv_last_timings(float* out_ms, int cap) {
     return n;
 }
 int rv_last_launch_count(void) { return t_launches; }
+int rv_last_passes(void) { return t_passes; }
 rv_status rv_dev_rebase_i32(int32_t* d_dst, const int32_t* d_src, int64_t n, int32_t add, void* cuda_stream) {
     if (n < 0 || (n > 0 && (!d_dst || !d_src))) return fail(RV_ERR_INVALID, "bad argument");
     launch_rebase_i32(d_dst, d_src, n, add, static_cast<cudaStream_t>(cuda_stream));
@@ -1091,11 +1344,20 @@ const char* rv_last_walker(void) { return t_walker; }
 const char* rv_schema_jit_status(const rv_schema* s) {
     if (!s) return "null schema";
     std::lock_guard<std::mutex> g(const_cast<rv_schema*>(s)->mu);
-    t_error = s->jit.tried ? s->jit.status : "not attempted yet";
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) (void)cudaGetLastError();
+    auto it = s->jit.find(device);
+    t_error = (it != s->jit.end() && it->second.tried) ? it->second.status : "not attempted yet";
     return t_error.c_str();
 }
-long long rv_last_overflow_tiles(void) { return t_overflow_tiles; }
+long long rv_last_slow_tiles(void) { return t_slow_tiles; }
 void rv_set_jit_enabled(int enabled) { g_jit_override.store(enabled < 0 ? -1 : (enabled ? 1 : 0)); }
+void rv_schema_forget_stats(const rv_schema* s_) {
+    rv_schema* s = const_cast<rv_schema*>(s_);
+    if (!s) return;
+    std::lock_guard<std::mutex> g(s->mu);
+    s->stats = SchemaStats();
+}
 
 int64_t rv_schema_walker_source(const rv_schema* s, char* buf, size_t cap) {
     if (!s || !s->has_plan) return -1;
@@ -1113,10 +1375,10 @@ rv_status rv_schema_precompile(const rv_schema* s, const char* arch) {
     if (st) return st;
     std::vector<char> cubin;
     std::string log;
-    if (!jit_cubin(generate_kernel_source(s->plan), arch && *arch ? arch : "sm_100a", &cubin, &log)) return fail(RV_ERR_CUDA, "NVRTC: " + log);
+    if (!jit_cubin(generate_kernel_source(s->plan), arch && *arch ? arch : "sm_100a", &cubin, &log, false)) return fail(RV_ERR_CUDA, "NVRTC: " + log);
     return RV_OK;
 }
 const char* rv_last_error(void) { return t_error.c_str(); }
-const char* rv_version(void) { return "pyruhvro_b200 0.1.0 (sm_100a)"; }
+const char* rv_version(void) { return "pyruhvro_b200 0.2.0 (sm_100a)"; }
 
 }  // extern "C"

@@ -18,11 +18,12 @@ namespace rv {
 // Source of `struct rv::gen::Walker` (includes only dev_core.cuh; also compiled for the host by tests/emu).
 std::string generate_walker_source(const Plan& plan);
 
-// Full NVRTC translation unit: walker + `rvj_count` / `rvj_emit` kernels.
+// Full NVRTC translation unit: walker + the `rvj_fused` kernel.
 std::string generate_kernel_source(const Plan& plan);
 
 // Compiles (or fetches from the on-disk cache) the cubin for `arch` (e.g. "sm_100a").
 // Needs no GPU.  Returns false and fills `log` when NVRTC cannot be loaded or compilation fails.
-bool jit_cubin(const std::string& source, const std::string& arch, std::vector<char>* cubin, std::string* log);
+// ignore_cache: recompile even if the on-disk cache holds an entry (it is replaced).
+bool jit_cubin(const std::string& source, const std::string& arch, std::vector<char>* cubin, std::string* log, bool ignore_cache = false);
 
 }  // namespace rv

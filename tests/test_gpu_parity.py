@@ -209,7 +209,7 @@ def test_i32_offset_ceiling_and_huge_records(coracle):
         s_col = b.column("s")
         assert s_col.buffers()[1].size >= 4 * 30_001 and s_col[29_999].as_py() == body.tobytes().decode()
         assert pa.compute.utf8_length(s_col).to_pylist()[:2] == [slen, slen]
-    assert pr.lib.rv_last_overflow_tiles() >= 0
+    assert pr.lib.rv_last_slow_tiles() >= 0
 
 
 def test_concurrent_calls_from_python_threads(coracle):
@@ -247,28 +247,79 @@ def test_error_surface():
         pr.deserialize_array([b""], "{not json")
 
 
-def test_specialised_emit_hands_unstageable_tiles_to_the_interpreter(coracle, monkeypatch):
-    """The generated emit kernel only runs tiles whose strings fit its staging area; with the staging area clamped
-    below the largest tile (RV_OUT_CLAMP) the rest must come out right through the interpreter's emit pass."""
+def test_tiles_that_do_not_fit_shared_memory_take_the_global_walk(coracle, monkeypatch, walker):
+    """The fused kernel walks a tile in shared memory when its bytes fit the input window and its strings the staging
+    area; with either window clamped below the largest tile (RV_OUT_CLAMP / RV_IN_CLAMP) the rest must come out right
+    through the in-kernel global-memory walk."""
     import workloads
     sj, data, off = workloads.generate("kafka", 60_000, seed=5)
-    pr.set_jit_enabled(1)
-    try:
-        monkeypatch.setenv("RV_OUT_CLAMP", "1.0")
-        got = pr.decode_packed(data, off, 60_000, sj, 3)
-        assert pr.last_walker() == "jit" and pr.lib.rv_last_overflow_tiles() > 0
-        assert_matches_oracle(coracle, got, sj, data, off, 60_000, 3)
-        monkeypatch.setenv("RV_IN_CLAMP", "1.0")     # and with the input window clamped too (count-phase overflow)
-        got = pr.decode_packed(data, off, 60_000, sj, 3)
-        assert pr.lib.rv_last_overflow_tiles() > 0
-        assert_matches_oracle(coracle, got, sj, data, off, 60_000, 3)
-    finally:
-        pr.set_jit_enabled(-1)
+    pr.decode_packed(data, off, 60_000, sj, 3)       # the schema handle now knows its sizes
+    monkeypatch.setenv("RV_OUT_CLAMP", "1.0")
+    got = pr.decode_packed(data, off, 60_000, sj, 3)
+    assert pr.last_walker() == walker and pr.lib.rv_last_slow_tiles() > 0
+    assert_matches_oracle(coracle, got, sj, data, off, 60_000, 3)
+    monkeypatch.setenv("RV_IN_CLAMP", "1.0")     # and with the input window clamped too
+    got = pr.decode_packed(data, off, 60_000, sj, 3)
+    assert pr.lib.rv_last_slow_tiles() > 0
+    assert_matches_oracle(coracle, got, sj, data, off, 60_000, 3)
+
+
+def test_capacity_plan_measures_first_then_runs_one_pass_and_repeats_when_outgrown(coracle, walker):
+    """Output buffers are sized from what earlier calls on the schema handle needed: the first call measures (2 passes),
+    the same data again takes 1 pass, and data whose strings are far longer than planned repeats once with exact sizes."""
+    sj = '{"type":"record","name":"C","fields":[{"name":"id","type":"long"},{"name":"s","type":["null","string"]},' \
+         '{"name":"xs","type":{"type":"array","items":"int"}}]}'
+    s = po.parse_schema(sj)
+    rng = random.Random(11)
+
+    def batch(n, slen, items):
+        recs = [po.encode_datum(s, {"id": i, "s": (0, None) if rng.random() < 0.3 else (1, "y" * rng.randrange(slen)), "xs": list(range(rng.randrange(items)))})
+                for i in range(n)]
+        return recs, *po.pack_records(recs)
+
+    schema = pr._get_or_parse_schema(sj)
+    pr.lib.rv_schema_forget_stats(schema.handle)
+    recs, data, off = batch(5000, 10, 3)
+    assert_matches_oracle(coracle, pr.decode_packed(data, off, len(recs), sj, 3), sj, data, off, len(recs), 3)
+    assert pr.lib.rv_last_passes() == 2
+    assert_matches_oracle(coracle, pr.decode_packed(data, off, len(recs), sj, 3), sj, data, off, len(recs), 3)
+    assert pr.lib.rv_last_passes() == 1
+    recs, data, off = batch(5000, 400, 40)            # 40x the bytes, 13x the child rows per record
+    assert_matches_oracle(coracle, pr.decode_packed(data, off, len(recs), sj, 3), sj, data, off, len(recs), 3)
+    assert pr.lib.rv_last_passes() == 2
+    assert_matches_oracle(coracle, pr.decode_packed(data, off, len(recs), sj, 3), sj, data, off, len(recs), 3)
+    assert pr.lib.rv_last_passes() == 1
+    recs, data, off = batch(700, 10, 3)               # smaller again: fits the larger plan
+    assert_matches_oracle(coracle, pr.decode_packed(data, off, len(recs), sj, 1), sj, data, off, len(recs), 1)
+    assert pr.lib.rv_last_passes() == 1
+
+
+@pytest.mark.parametrize("name,n,k", [("kafka", 10_000_000, 8), ("flat", 2_000_000, 8), ("wide", 2_000_000, 8)])
+def test_bench_scale_parity(coracle, name, n, k):
+    """The configurations bench.py times (C3 at 10 M records / 8 chunks; C2 and C4 at 2 M), every exported buffer of
+    every batch compared with the C oracle — through the host C ABI and through the device-resident path."""
+    import ctypes
+    import torch
+    import workloads
+    sj, data, off = workloads.generate(name, n, seed=42)
+    got = pr.decode_packed(data, off, n, sj, k)
+    assert_matches_oracle(coracle, got, sj, data, off, n, k, full_validate=False)
+    del got
+    # device-resident decode (what bench.py's `value` times), brought to the host afterwards
+    schema = pr._get_or_parse_schema(sj)
+    total = int(off[n])
+    d_data = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
+    d_data[:total].copy_(torch.from_numpy(data))
+    d_off = torch.from_numpy(off).cuda()
+    h = ctypes.c_void_p()
+    pr._check(pr.lib.rv_decode_device(schema.handle, d_data.data_ptr(), d_off.data_ptr(), n, k, torch.cuda.current_stream().cuda_stream, ctypes.byref(h)))
+    assert pr.lib.rv_last_passes() == 1 and pr.lib.rv_last_slow_tiles() == 0
+    pr._check(pr.lib.rv_result_to_host(h))
+    assert_matches_oracle(coracle, pr._export_batches(h.value, schema), sj, data, off, n, k, full_validate=False)
 
 
 def test_large_records_use_global_path(coracle, walker):
-    """Records far larger than the shared-memory tile exercise the direct-from-global walk; under the
-    specialised kernels those tiles are routed to the interpreter kernels through the overflow list."""
+    """Records far larger than the shared-memory tile exercise the direct-from-global walk inside the fused kernel."""
     sj = '{"type":"record","name":"L","fields":[{"name":"s","type":"string"},{"name":"a","type":{"type":"array","items":"long"}}]}'
     s = po.parse_schema(sj)
     rng = random.Random(9)

@@ -4,7 +4,7 @@
 
 Each combination of the listed environment variables gets a fresh Schema handle (the knobs are read at kernel
 generation time and are part of the cubin cache key), 3 warm-up + 20 timed rv_decode_device calls, and one line
-with the count / emit kernel times from rv_last_timings.  Development tool; needs a GPU.
+with the fused kernel's time from rv_last_timings.  Development tool; needs a GPU.
 """
 import argparse
 import ctypes
@@ -63,8 +63,8 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
         kt /= args.steps
-        print(dict(zip(names, combo)), f"step {ms:.3f} ms  {n / ms / 1e6:.2f} G rec/s  count {kt[0]:.3f}  scan {kt[1]:.3f}  "
-              f"emit {kt[2]:.3f}  walker {pr.last_walker()}  overflow {L.rv_last_overflow_tiles()}", flush=True)
+        print(dict(zip(names, combo)), f"step {ms:.3f} ms  {n / ms / 1e6:.2f} G rec/s  fused {kt[0]:.3f}  extra-pass {kt[1]:.3f}  "
+              f"nullcount {kt[3]:.3f}  walker {pr.last_walker()}  passes {L.rv_last_passes()}  slow tiles {L.rv_last_slow_tiles()}", flush=True)
 
 
 if __name__ == "__main__":

@@ -23,6 +23,8 @@ def schemas():
     out.append('{"type":"record","name":"L","fields":[{"name":"s","type":"string"},{"name":"a","type":{"type":"array","items":"long"}}]}')
     out.append('{"type":"record","name":"Z","fields":[{"name":"z","type":{"type":"array","items":"null"}},'
                '{"name":"m","type":{"type":"map","values":{"type":"array","items":{"type":"array","items":["null","string"]}}}}]}')
+    out.append('{"type":"record","name":"C","fields":[{"name":"id","type":"long"},{"name":"s","type":["null","string"]},'
+               '{"name":"xs","type":{"type":"array","items":"int"}}]}')
     return list(dict.fromkeys(out))
 
 
