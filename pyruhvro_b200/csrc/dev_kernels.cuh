@@ -203,22 +203,25 @@ __device__ __forceinline__ void wait_window(const TileWindow& w, const SmemMap& 
 template <class C>
 __device__ __forceinline__ int64_t init_ctx(C& c, const DecodeParams& p, const Tile& t, const SmemMap& m, const TileWindow& w) {
     const int tid = threadIdx.x;
+    const uint32_t s0 = smem_addr(rv_smem);
     c.nodes = reinterpret_cast<const DNode*>(rv_smem + m.nodes);
     c.cur = reinterpret_cast<uint32_t*>(rv_smem + m.cur) + tid;
+    c.cur_stride = kBlock;
     c.sym_off = p.sym_off;
     c.sym_bytes = p.sym_bytes;
     c.bufs = p.bufs ? p.bufs + size_t(t.chunk) * p.n_slots : nullptr;
-    c.ptrs_soff = p.bufs ? m.ptrs : 0u;
+    c.ptrs_saddr = p.bufs ? s0 + m.ptrs : 0u;
     c.err = 0;
     c.pm = 0;
     c.usel = 0;
-    c.stage_soff = m.stage;
-    c.stage_adj = reinterpret_cast<const uint32_t*>(rv_smem + m.adj);
+    c.stage_on = false;
+    c.stage_saddr = s0 + m.stage;
+    c.adj_saddr = s0 + m.adj;
     c.in_range = tid < t.nrec;
     c.row0 = uint32_t(t.local_tile) * kBlock + tid;
     c.store_word = (tid & 31) == 0 && int64_t(c.row0) < t.chunk_len;
     c.base = p.data;
-    c.soff = m.in;
+    c.sbase = s0 + m.in;
     c.pos = c.end = 0;
     const int64_t r = t.r0 + tid;
     if (c.in_range) {
@@ -250,8 +253,9 @@ __device__ __forceinline__ void prefetch_window(const DecodeParams& p, const Til
 }
 
 // ---- count ----------------------------------------------------------------------------------
-// Returns this lane's error code.  (Never inlined for the global-memory window: that instantiation only runs for
-// tiles that do not fit shared memory and must not cost the common path registers.)
+// SM = true, the FAST flavour: returns != 0 when the record is not plain (dev_core.cuh) and reports nothing — the
+// caller repeats the record with the precise flavour.  SM = false, PRECISE: reports the record's first error and
+// returns its code.
 template <class W, bool SM>
 __device__ __forceinline__ uint32_t count_walk(const DecodeParams& p, const Tile& t, const SmemMap& m, const TileWindow& w, typename W::Cur& q) {
     WalkCtx<SM> c;
@@ -259,11 +263,13 @@ __device__ __forceinline__ uint32_t count_walk(const DecodeParams& p, const Tile
     if constexpr (W::kRegCursors) {
 #pragma unroll
         for (int s = 0; s < W::kStreams; ++s) q.v[s] = 0;
+    } else {
+        if (!SM) for (int s = 0; s < p.n_streams; ++s) c.cur[s * kBlock] = 0;  // (a fast walk may have left partial counts)
     }
 #if !defined(RV_ABL_NOCOUNTWALK)
     W::template walk<WM_COUNT>(c, p.n_nodes, q);
 #endif
-    if (c.in_range && c.err) report(p, r, c.err);
+    if (!SM && c.in_range && c.err) report(p, r, c.err);
     return c.in_range ? c.err : 0u;
 }
 // Everything by value: a reference parameter of a function that is not inlined would force the caller's copy (the
@@ -315,20 +321,21 @@ __device__ __forceinline__ void stage_map(const DecodeParams& p, const Tile& t, 
 
 // ---- emit -----------------------------------------------------------------------------------
 template <class W, bool SM>
-__device__ __forceinline__ void emit_walk(const DecodeParams& p, const Tile& t, const SmemMap& m, const TileWindow& w, typename W::Cur& q) {
+__device__ __forceinline__ void emit_walk(const DecodeParams& p, const Tile& t, const SmemMap& m, const TileWindow& w, typename W::Cur& q, const bool stage_on) {
     WalkCtx<SM> c;
     (void)init_ctx(c, p, t, m, w);
+    c.stage_on = stage_on;
     const int tid = threadIdx.x;
     // offsets[0] = 0 of every offsets buffer of this chunk (first tile of the chunk only)
     if (t.local_tile == 0) {
         if (p.n_nodes) {
-            for (int i = tid; i < p.n_nodes; i += kBlock) {
+            for (int i = tid & 31; i < p.n_nodes; i += 32) {  // (every warp: a warp may be alone on the precise path)
                 const DNode nd = c.nodes[i];
                 if (nd.kind == NK_STR || nd.kind == NK_ENUM || nd.kind == NK_LIST || nd.kind == NK_MAP || nd.kind == NK_BYTES)
                     static_cast<int32_t*>(buf_ptr(c, nd.slot_a))[0] = 0;
             }
         } else {
-            W::zero_offsets(c, tid);
+            W::zero_offsets(c, tid & 31);
         }
     }
 #if !defined(RV_ABL_NOWALK)
@@ -336,8 +343,8 @@ __device__ __forceinline__ void emit_walk(const DecodeParams& p, const Tile& t, 
 #endif
 }
 template <class W>
-__device__ __noinline__ void emit_walk_global(const DecodeParams p, const Tile t, const SmemMap m, const TileWindow w, typename W::Cur q) {
-    emit_walk<W, false>(p, t, m, w, q);
+__device__ __noinline__ void emit_walk_global(const DecodeParams p, const Tile t, const SmemMap m, const TileWindow w, typename W::Cur q, const bool stage_on) {
+    emit_walk<W, false>(p, t, m, w, q, stage_on);
 }
 
 // Coalesced write-out of the staged Utf8 bytes, one warp per stream at a time.
@@ -383,10 +390,21 @@ __device__ __forceinline__ void fused_body(const DecodeParams& p, const int tile
     __syncthreads();
     wait_window(w, m);
 
-    // ---- COUNT: validation + what this record adds to every stream
+    // ---- COUNT: validation + what this record adds to every stream.  Records that are not plain (non-canonical
+    // encodings, or malformed) are repeated by their lane with the precise walker, which settles what they are; their
+    // warp then also emits with the precise walker.
     uint32_t my_err;
-    if (w.staged) my_err = count_walk<W, true>(p, t, m, w, q);
-    else {
+    bool warp_precise = false;
+    if (w.staged) {
+        my_err = count_walk<W, true>(p, t, m, w, q);
+        const bool not_plain = my_err != 0u;
+        if (not_plain) {
+            const CountOut<W> o = count_walk_global<W>(p, t, m, w);
+            q = o.q;
+            my_err = o.err;
+        }
+        warp_precise = __any_sync(0xFFFFFFFFu, not_plain);
+    } else {
         const CountOut<W> o = count_walk_global<W>(p, t, m, w);
         q = o.q;
         my_err = o.err;
@@ -508,14 +526,15 @@ __device__ __forceinline__ void fused_body(const DecodeParams& p, const int tile
     __syncthreads();
     const bool fast = w.staged && (flags[0] & 2u);
     if (fast) {
-        emit_walk<W, true>(p, t, m, w, q);
+        if (!warp_precise) emit_walk<W, true>(p, t, m, w, q, true);
+        else emit_walk_global<W>(p, t, m, w, q, true);  // (warp-uniform) stages its strings like the other warps
         prefetch_window(p, w);
         if (p.n_utf8 > 0) stage_write_out(p, m);
     } else {
         // the tile's bytes or its strings do not fit shared memory: walk the records in global memory and write
         // strings straight to their Arrow buffers (slow; window sizing keeps such tiles rare)
         if (tid == 0) atomicAdd(p.ctrl + CW_SLOW_TILES, 1ull);
-        emit_walk_global<W>(p, t, m, w, q);
+        emit_walk_global<W>(p, t, m, w, q, false);
     }
 }
 

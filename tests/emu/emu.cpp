@@ -44,7 +44,8 @@ std::vector<Tile> make_tiles(int64_t n, int k) {
     return t;
 }
 
-using Ctx = WalkCtx<false>;
+using Ctx = WalkCtx<false>;      // PRECISE flavour: reads the record where it lies
+using FastCtx = WalkCtx<true>;   // FAST flavour: reads a padded copy of the tile's byte window, like the staged shared-memory window
 
 // register-cursor walkers exchange their cursors with the emulation's cur[stream][lane] table
 template <class Q>
@@ -56,17 +57,23 @@ void load_cursors(Q& q, const uint32_t* cur_lane, int S) {
     if constexpr (EmuWalker::kRegCursors) for (int s = 0; s < S; ++s) q.v[s] = cur_lane[size_t(s) * kTile];
 }
 
-void init_ctx(Ctx& c, const Plan& plan, const uint8_t* data, const int64_t* off, const Tile& t, int lane,
-              uint32_t* cur, int S, void* const* bufs) {
+template <class C>
+void init_common(C& c, const Plan& plan, const Tile& t, int lane, uint32_t* cur, void* const* bufs) {
     std::memset(&c, 0, sizeof c);
     c.nodes = plan.nodes.data();
     c.cur = cur + lane;
+    c.cur_stride = kTile;
     c.sym_off = plan.sym_off.data();
     c.sym_bytes = plan.sym_bytes.data();
     c.bufs = bufs;
     c.in_range = lane < t.nrec;
     c.row0 = uint32_t(t.local) * kTile + uint32_t(lane);
     c.store_word = false;
+}
+
+void init_ctx(Ctx& c, const Plan& plan, const uint8_t* data, const int64_t* off, const Tile& t, int lane,
+              uint32_t* cur, int S, void* const* bufs) {
+    init_common(c, plan, t, lane, cur, bufs);
     (void)S;
     if (c.in_range) {
         const int64_t r = t.r0 + lane;
@@ -74,6 +81,57 @@ void init_ctx(Ctx& c, const Plan& plan, const uint8_t* data, const int64_t* off,
         c.pos = 0;
         c.end = uint32_t(off[r + 1] - off[r]);
     }
+}
+
+// The tile's bytes followed by kWindowPad bytes of junk (the device leaves whatever was in shared memory there).
+std::vector<uint8_t> make_window(const uint8_t* data, const int64_t* off, const Tile& t) {
+    const int64_t t0 = off[t.r0], t1 = off[t.r0 + t.nrec];
+    std::vector<uint8_t> w(size_t(t1 - t0) + kWindowPad, uint8_t(0xA5));
+    if (t1 > t0) std::memcpy(w.data(), data + t0, size_t(t1 - t0));
+    return w;
+}
+
+void init_fast(FastCtx& c, const Plan& plan, const std::vector<uint8_t>& window, const int64_t* off, const Tile& t, int lane,
+               uint32_t* cur, void* const* bufs) {
+    init_common(c, plan, t, lane, cur, bufs);
+    c.base = window.data();
+    if (c.in_range) {
+        const int64_t r = t.r0 + lane, t0 = off[t.r0];
+        c.pos = uint32_t(off[r] - t0);
+        c.end = uint32_t(off[r + 1] - t0);
+    }
+}
+
+// COUNT of one tile the way fused_body does it: every lane walks FAST; a lane whose record is not plain repeats it
+// PRECISE (which alone decides errors); a 32-lane "warp" with any such lane is marked for the precise EMIT.
+// Returns the first error's lane or -1.
+int count_tile(const Plan& plan, const uint8_t* data, const int64_t* off, const Tile& t, int S, std::vector<uint32_t>& cur,
+               bool* warp_precise, uint32_t* err_code, long long* fast_lanes, long long* precise_lanes) {
+    std::fill(cur.begin(), cur.end(), 0u);
+    const std::vector<uint8_t> window = make_window(data, off, t);
+    for (int w = 0; w < kTile / 32; ++w) warp_precise[w] = false;
+    for (int lane = 0; lane < kTile; ++lane) {
+        FastCtx f;
+        init_fast(f, plan, window, off, t, lane, cur.data(), nullptr);
+        EmuWalker::Cur q{};
+        EmuWalker::walk<WM_COUNT>(f, int(plan.nodes.size()), q);
+        if (f.in_range && f.pos > f.end + kWindowPad) { std::fprintf(stderr, "emu: fast reader ran %u bytes past the record\n", f.pos - f.end); std::abort(); }
+        if (f.in_range && f.err) {
+            warp_precise[lane / 32] = true;
+            for (int s = 0; s < S; ++s) cur[size_t(s) * kTile + lane] = 0;
+            Ctx c;
+            init_ctx(c, plan, data, off, t, lane, cur.data(), S, nullptr);
+            q = EmuWalker::Cur{};
+            EmuWalker::walk<WM_COUNT>(c, int(plan.nodes.size()), q);
+            store_cursors(q, cur.data() + lane, S);
+            if (precise_lanes) ++*precise_lanes;
+            if (c.err) { *err_code = c.err; return lane; }
+        } else {
+            store_cursors(q, cur.data() + lane, S);
+            if (fast_lanes && f.in_range) ++*fast_lanes;
+        }
+    }
+    return -1;
 }
 }  // namespace
 
@@ -97,16 +155,14 @@ int emu_decode(const char* json, size_t len, const uint8_t* data, const int64_t*
         std::vector<uint32_t> cur(size_t(S1) * kTile);
         std::vector<std::vector<uint32_t>> tile_agg(tiles.size(), std::vector<uint32_t>(size_t(S1), 0));
         // ---- count pass ----
+        std::vector<char> precise_warp(tiles.size() * size_t(kTile / 32), 0);
+        long long fast_lanes = 0, precise_lanes = 0;
         for (size_t ti = 0; ti < tiles.size(); ++ti) {
-            std::fill(cur.begin(), cur.end(), 0u);
-            for (int lane = 0; lane < kTile; ++lane) {
-                Ctx c;
-                init_ctx(c, plan, data, off, tiles[ti], lane, cur.data(), S, nullptr);
-                EmuWalker::Cur q{};
-                EmuWalker::walk<WM_COUNT>(c, int(plan.nodes.size()), q);
-                store_cursors(q, cur.data() + lane, S);
-                if (c.in_range && c.err) { *err_record = tiles[ti].r0 + lane; return int(c.err); }
-            }
+            bool wp[kTile / 32];
+            uint32_t code = 0;
+            const int bad = count_tile(plan, data, off, tiles[ti], S, cur, wp, &code, &fast_lanes, &precise_lanes);
+            if (bad >= 0) { *err_record = tiles[ti].r0 + bad; return int(code); }
+            for (int w = 0; w < kTile / 32; ++w) precise_warp[ti * size_t(kTile / 32) + size_t(w)] = wp[w];
             for (int s = 0; s < S; ++s) {
                 uint64_t sum = 0;
                 for (int lane = 0; lane < kTile; ++lane) sum += cur[size_t(s) * kTile + lane];
@@ -114,6 +170,7 @@ int emu_decode(const char* json, size_t len, const uint8_t* data, const int64_t*
                 tile_agg[ti][size_t(s)] = uint32_t(sum);
             }
         }
+        if (std::getenv("EMU_TRACE")) std::fprintf(stderr, "emu: %lld fast lanes, %lld precise lanes\n", fast_lanes, precise_lanes);
         // ---- per-chunk scan ----
         std::vector<unsigned long long> chunk_tot(size_t(k) * size_t(S1), 0ull);
         std::vector<std::vector<uint32_t>> tile_base(tiles.size(), std::vector<uint32_t>(size_t(S1), 0));
@@ -140,27 +197,29 @@ int emu_decode(const char* json, size_t len, const uint8_t* data, const int64_t*
         for (size_t ti = 0; ti < tiles.size(); ++ti) {
             const Tile& t = tiles[ti];
             void* const* cb = bufs.data() + size_t(t.chunk) * size_t(n_slots);
-            std::fill(cur.begin(), cur.end(), 0u);
-            for (int lane = 0; lane < kTile; ++lane) {
-                Ctx c;
-                init_ctx(c, plan, data, off, t, lane, cur.data(), S, nullptr);
-                EmuWalker::Cur q{};
-                EmuWalker::walk<WM_COUNT>(c, int(plan.nodes.size()), q);
-                store_cursors(q, cur.data() + lane, S);
-            }
+            bool wp[kTile / 32];
+            uint32_t code = 0;
+            (void)count_tile(plan, data, off, t, S, cur, wp, &code, nullptr, nullptr);
             for (int s = 0; s < S; ++s) {  // exclusive scan across lanes + tile base
                 uint32_t run = tile_base[ti][size_t(s)];
                 for (int lane = 0; lane < kTile; ++lane) { uint32_t v = cur[size_t(s) * kTile + lane]; cur[size_t(s) * kTile + lane] = run; run += v; }
             }
             if (t.local == 0)
                 for (const DNode& nd : plan.nodes)
-                    if (nd.kind == NK_STR || nd.kind == NK_ENUM || nd.kind == NK_LIST || nd.kind == NK_MAP) static_cast<int32_t*>(cb[nd.slot_a])[0] = 0;
+                    if (nd.kind == NK_STR || nd.kind == NK_ENUM || nd.kind == NK_LIST || nd.kind == NK_MAP || nd.kind == NK_BYTES) static_cast<int32_t*>(cb[nd.slot_a])[0] = 0;
+            const std::vector<uint8_t> window = make_window(data, off, t);
             for (int lane = 0; lane < kTile; ++lane) {
-                Ctx c;
-                init_ctx(c, plan, data, off, t, lane, cur.data(), S, cb);
                 EmuWalker::Cur q{};
                 load_cursors(q, cur.data() + lane, S);
-                EmuWalker::walk<WM_EMIT>(c, int(plan.nodes.size()), q);
+                if (wp[lane / 32]) {  // a warp with a record that is not plain emits with the precise walker
+                    Ctx c;
+                    init_ctx(c, plan, data, off, t, lane, cur.data(), S, cb);
+                    EmuWalker::walk<WM_EMIT>(c, int(plan.nodes.size()), q);
+                } else {
+                    FastCtx f;
+                    init_fast(f, plan, window, off, t, lane, cur.data(), cb);
+                    EmuWalker::walk<WM_EMIT>(f, int(plan.nodes.size()), q);
+                }
             }
         }
         // ---- null counts ----
