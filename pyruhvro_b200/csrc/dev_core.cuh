@@ -198,7 +198,8 @@ RV_HD bool rd_len(C& c, uint32_t& len) {
         }
         len = z >> 1;
         // negative, or longer than what is left of the record (pos may already be past the end; len < 2^31)
-        if (CHECK && ((z & 1u) || uint64_t(c.pos) + len > uint64_t(c.end))) { c.err |= E_EOF; len = 0; }
+        // (32-bit sum: pos stays within the window + pad, far below 2^31)
+        if (CHECK && ((z & 1u) || c.pos + len > c.end)) { c.err |= E_EOF; len = 0; }
         return true;
     }
     bool have = false;

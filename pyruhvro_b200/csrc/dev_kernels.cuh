@@ -31,22 +31,35 @@ namespace rv {
 struct Tile {
     int chunk;
     int local_tile;
+    int lin;             // chunk * tiles_per_chunk + local_tile: index of the tile's scan status words
     int64_t r0;          // first record of the tile
     int nrec;            // records in the tile
     int64_t chunk_len;   // rows in the chunk
 };
 
-__device__ __forceinline__ Tile tile_of(const DecodeParams& p, int tile) {
+// blockIdx -> tile.  CTAs are dispatched in blockIdx order and every chunk (output batch) is its own look-back
+// chain, so consecutive CTAs take tiles of DIFFERENT chunks (id = local * k + chunk): the k chains advance side by
+// side instead of one after the other, which multiplies the rate at which prefixes become known and divides how many
+// running predecessors a tile can be held up by.  (The last chunk is the longest — it takes the remainder rows — and
+// its surplus tiles come last.)
+__device__ __forceinline__ Tile tile_of(const DecodeParams& p, int id) {
     Tile t;
-    int j = 0;
-    if (p.k > 1) {  // tile / tiles_per_chunk without the ~40-instruction integer division: estimate and correct
-        j = int(__fdividef(float(tile), float(p.tiles_per_chunk)));
-        while (j > 0 && j * p.tiles_per_chunk > tile) --j;
-        while ((j + 1) * p.tiles_per_chunk <= tile) ++j;
-        if (j > p.k - 1) j = p.k - 1;
+    int j = 0, local = id;
+    if (p.k > 1) {
+        const int body = p.k * p.tiles_per_chunk;
+        if (id < body) {  // id / k without the ~40-instruction integer division: estimate and correct
+            local = int(__fdividef(float(id), float(p.k)));
+            while (local > 0 && local * p.k > id) --local;
+            while ((local + 1) * p.k <= id) ++local;
+            j = id - local * p.k;
+        } else {
+            j = p.k - 1;
+            local = p.tiles_per_chunk + (id - body);
+        }
     }
     t.chunk = j;
-    t.local_tile = tile - j * p.tiles_per_chunk;
+    t.local_tile = local;
+    t.lin = j * p.tiles_per_chunk + local;
     const int64_t cs = int64_t(j) * p.chunk_rows;
     const int64_t ce = (j == p.k - 1) ? p.n : cs + p.chunk_rows;
     t.chunk_len = ce - cs;
@@ -189,8 +202,8 @@ __device__ __forceinline__ TileWindow stage_in(const DecodeParams& p, const Tile
     }
     if (tid == 0) {  // window sizing of later calls: the largest tile seen, the input's byte span
         if (span > 0 && static_cast<unsigned long long>(span) > p.ctrl[CW_MAX_SPAN]) atomicMax(p.ctrl + CW_MAX_SPAN, static_cast<unsigned long long>(span));
-        if (tile_id == 0) p.ctrl[CW_IN_FIRST] = static_cast<unsigned long long>(w.t0);
-        if (tile_id == p.n_tiles - 1) p.ctrl[CW_IN_LAST] = static_cast<unsigned long long>(w.t1);
+        if (t.lin == 0) p.ctrl[CW_IN_FIRST] = static_cast<unsigned long long>(w.t0);
+        if (t.lin == p.n_tiles - 1) p.ctrl[CW_IN_LAST] = static_cast<unsigned long long>(w.t1);
     }
     return w;
 }
@@ -472,7 +485,7 @@ __device__ __forceinline__ void fused_body(const DecodeParams& p, const int tile
         // publish right away: the successors' look-backs are waiting for it
         if (lane == 0) {
             ttot[s] = tile_total;
-            st_state(p.tile_state + size_t(s) * p.n_tiles + tile_id, (t.local_tile == 0 ? kStPrefix : kStAgg) | tile_total);
+            st_state(p.tile_state + size_t(s) * p.n_tiles + t.lin, (t.local_tile == 0 ? kStPrefix : kStAgg) | tile_total);
         }
     }
     // ---- chain the tile totals: exclusive prefix within the chunk
@@ -481,8 +494,10 @@ __device__ __forceinline__ void fused_body(const DecodeParams& p, const int tile
         const uint32_t tot = ttot[s];
         if (t.local_tile != 0) {
             unsigned long long* st = p.tile_state + size_t(s) * p.n_tiles;
-            base = look_back(st, tile_id, tile_id - t.local_tile);
-            if (lane == 0) st_state(st + tile_id, kStPrefix | ((base + tot) & kStMask));
+#if !defined(RV_ABL_NOLOOKBACK)
+            base = look_back(st, t.lin, t.lin - t.local_tile);
+#endif
+            if (lane == 0) st_state(st + t.lin, kStPrefix | ((base + tot) & kStMask));
         }
         if (lane == 0) {
             const unsigned long long incl = base + tot;
