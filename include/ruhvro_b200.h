@@ -124,6 +124,9 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
 int64_t rv_encoded_num_chunks(const rv_encoded* r);
 rv_status rv_encoded_export(rv_encoded* r, int64_t chunk, struct ArrowArray* out_array, struct ArrowSchema* out_schema);
 void rv_encoded_free(rv_encoded* r);
+/* CUDA-event timings of the calling thread's last encode, in milliseconds: [0] size kernel, [1] scan, [2] write kernel,
+ * [3] upload of the Arrow buffers, [4] download of the datums.  Returns how many entries were written. */
+int rv_last_encode_timings(float* out_ms, int cap);
 
 /* ---- multi-GPU: fix-ups for gathering shard-local batches into ONE RecordBatch -------------------------
  * Records shard by message; each rank decodes its contiguous range (exactly the reference's per-chunk batches,

@@ -37,6 +37,7 @@
  */
 #define _GNU_SOURCE
 #include <pthread.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -740,9 +741,23 @@ void orc_chunk_bounds(int64_t n, int64_t k, int64_t i, int64_t *r0, int64_t *r1)
     *r0 = i * cs; *r1 = (i == k - 1) ? n : (i + 1) * cs;
 }
 
-typedef struct { const orc_schema *s; const uint8_t *data; const int64_t *offsets; int64_t n, k; int64_t next; pthread_mutex_t mu; orc_batch **out; } job;
+/* Benchmark aid: orc_set_pin(1) pins worker t of orc_decode_threaded to the t-th CPU of the process's affinity mask
+ * (steadier timings of the CPU arm on shared boxes).  Off by default. */
+static int g_pin = 0;
+void orc_set_pin(int on) { g_pin = on; }
+
+typedef struct { const orc_schema *s; const uint8_t *data; const int64_t *offsets; int64_t n, k; int64_t next; pthread_mutex_t mu; orc_batch **out;
+                 int next_thread; cpu_set_t allowed; int n_allowed; } job;
 static void *worker(void *arg) {
     job *j = arg;
+    if (g_pin && j->n_allowed > 0) {
+        pthread_mutex_lock(&j->mu); int me = j->next_thread++; pthread_mutex_unlock(&j->mu);
+        int want = me % j->n_allowed, seen = 0;
+        for (int c = 0; c < CPU_SETSIZE; c++) {
+            if (!CPU_ISSET(c, &j->allowed)) continue;
+            if (seen++ == want) { cpu_set_t one; CPU_ZERO(&one); CPU_SET(c, &one); pthread_setaffinity_np(pthread_self(), sizeof one, &one); break; }
+        }
+    }
     for (;;) {
         pthread_mutex_lock(&j->mu); int64_t i = j->next++; pthread_mutex_unlock(&j->mu);
         if (i >= j->k) return NULL;
@@ -755,7 +770,10 @@ static void *worker(void *arg) {
 int64_t orc_decode_threaded(const orc_schema *s, const uint8_t *data, const int64_t *offsets, int64_t n,
                             int64_t num_chunks, int threads, orc_batch **out) {
     int64_t k = orc_clamp_chunks(num_chunks, n);
-    job j = { s, data, offsets, n, k, 0, PTHREAD_MUTEX_INITIALIZER, out };
+    job j = { s, data, offsets, n, k, 0, PTHREAD_MUTEX_INITIALIZER, out, 0 };
+    CPU_ZERO(&j.allowed);
+    j.n_allowed = 0;
+    if (g_pin && sched_getaffinity(0, sizeof j.allowed, &j.allowed) == 0) j.n_allowed = CPU_COUNT(&j.allowed);
     if (threads < 1) threads = 1;
     if (threads > k) threads = (int)k;
     pthread_t *th = xmalloc(sizeof(pthread_t) * (size_t)threads);

@@ -789,6 +789,8 @@ class COracle:
         L.orc_decode_threaded.restype = ctypes.c_int64
         L.orc_decode_threaded.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                           ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
+        L.orc_set_pin.argtypes = [ctypes.c_int]
+        L.orc_set_pin.restype = None
         L.orc_clamp_chunks.restype = ctypes.c_int64
         L.orc_clamp_chunks.argtypes = [ctypes.c_int64, ctypes.c_int64]
         L.orc_batch_free.argtypes = [ctypes.c_void_p]

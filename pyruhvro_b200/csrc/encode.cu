@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -553,6 +554,13 @@ void release_static_schema(ArrowSchema* s) { s->release = nullptr; }
 extern "C" {
 
 // Replaces ruhvro::serialize::serialize_record_batch (ruhvro/src/serialize.rs:38-67).
+static thread_local float t_enc_timings[5] = {0, 0, 0, 0, 0};
+extern "C" int rv_last_encode_timings(float* out_ms, int cap) {
+    const int n = cap < 5 ? cap : 5;
+    for (int i = 0; i < n; ++i) out_ms[i] = t_enc_timings[i];
+    return n;
+}
+
 rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct ArrowSchema* batch_schema, int64_t num_chunks, rv_encoded** out) {
     if (!s || !batch || !batch_schema || !out) { rv_set_last_error("null argument"); return RV_ERR_INVALID; }
     *out = nullptr;
@@ -574,6 +582,16 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
         trace_line += std::string(what) + "=" + std::to_string(std::chrono::duration<double, std::milli>(now - t_prev).count()).substr(0, 6) + "ms ";
         t_prev = now;
     };
+    // CUDA-event timings of this call (rv_last_encode_timings): [0] size kernel, [1] scan (+ tile max), [2] write kernel,
+    // [3] upload of the Arrow buffers, [4] download of the datums
+    struct Ev {
+        cudaEvent_t e[8] = {};
+        Ev() { for (auto& x : e) if (cudaEventCreate(&x) != cudaSuccess) x = nullptr; }
+        ~Ev() { for (auto& x : e) if (x) cudaEventDestroy(x); (void)cudaGetLastError(); }
+        void rec(int i) { if (e[i]) cudaEventRecord(e[i], nullptr); }
+        float ms(int a, int b_) { float t = 0; if (e[a] && e[b_] && cudaEventElapsedTime(&t, e[a], e[b_]) == cudaSuccess) return t; (void)cudaGetLastError(); return 0; }
+    } ev;
+    for (float& t : t_enc_timings) t = 0;
     EncBuilder b;
     try {
         b.record_children(*top, batch, batch_schema, batch->offset, 1, 0, 0);
@@ -597,6 +615,7 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
     for (size_t i = 0; i < b.bufs.size(); ++i) { boff[i] = total; total += (b.bufs[i].bytes + 8 + 63) & ~size_t(63); }
     DevMem d_in, d_nodes, d_symoff, d_symbytes, d_rowsize, d_agg, d_base, d_err, d_tot, d_ptrs;
     ENC_CUDA(d_in.alloc(total));
+    ev.rec(0);
     // The caller's Arrow buffers are ordinary pageable memory: copying them to the device directly runs at a
     // fraction of PCIe speed (the driver stages every piece itself, serially).  Instead a few host threads gather
     // 16 MiB pieces into one pinned arena (same layout as the device arena) and each piece's H2D copy is issued as
@@ -658,6 +677,7 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
     if (!b.sym_off.empty()) ENC_CUDA(cudaMemcpyAsync(d_symoff.p, b.sym_off.data(), b.sym_off.size() * 4, cudaMemcpyHostToDevice, nullptr));
     if (!b.sym_bytes.empty()) ENC_CUDA(cudaMemcpyAsync(d_symbytes.p, b.sym_bytes.data(), b.sym_bytes.size(), cudaMemcpyHostToDevice, nullptr));
 
+    ev.rec(1);
     mark("upload");
     EncParams p{};
     p.nodes = static_cast<const ENode*>(d_nodes.p); p.n_nodes = int32_t(b.nodes.size());
@@ -679,12 +699,14 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
         p.row_size = static_cast<uint32_t*>(d_rowsize.p); p.tile_agg = static_cast<uint32_t*>(d_agg.p);
         p.tile_base = static_cast<uint32_t*>(d_base.p); p.err = static_cast<unsigned long long*>(d_err.p);
         encode_size_kernel<<<unsigned(n_tiles), kBlock>>>(p);
+        ev.rec(2);
         int thr = 32;
         while (thr < 1024 && thr < tpc) thr <<= 1;
         encode_scan_kernel<<<unsigned(k), thr>>>(p, static_cast<unsigned long long*>(d_tot.p));
         ENC_CUDA(cudaMemsetAsync(static_cast<uint8_t*>(d_err.p) + 8, 0, 8, nullptr));
         encode_tile_max_kernel<<<std::max(1, std::min(int((n_tiles + 255) / 256), 592)), 256>>>(p, static_cast<unsigned long long*>(d_err.p) + 1);
         ENC_CUDA(cudaGetLastError());
+        ev.rec(3);
         unsigned long long err_word = ~0ull;
         ENC_CUDA(cudaMemcpyAsync(&max_tile, static_cast<uint8_t*>(d_err.p) + 8, 8, cudaMemcpyDeviceToHost, nullptr));
         ENC_CUDA(cudaMemcpyAsync(&err_word, d_err.p, 8, cudaMemcpyDeviceToHost, nullptr));
@@ -723,18 +745,28 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
         // staging area: the largest tile (+ alignment), capped so at least two CTAs share an SM
         size_t stage = std::min<size_t>(size_t(max_tile) + 32, 100 * 1024);
         stage = (stage + 63) & ~size_t(63);
-        static bool attr_set = false;
-        if (!attr_set) {
-            ENC_CUDA(cudaFuncSetAttribute(encode_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-            ENC_CUDA(cudaFuncSetAttribute(encode_write_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            attr_set = true;
+        {   // function attributes are per device
+            static std::mutex attr_mu;
+            static std::vector<char> attr_set;
+            int dev_now = 0;
+            ENC_CUDA(cudaGetDevice(&dev_now));
+            std::lock_guard<std::mutex> g(attr_mu);
+            if (attr_set.size() <= size_t(dev_now)) attr_set.resize(size_t(dev_now) + 1, 0);
+            if (!attr_set[size_t(dev_now)]) {
+                ENC_CUDA(cudaFuncSetAttribute(encode_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+                ENC_CUDA(cudaFuncSetAttribute(encode_write_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                attr_set[size_t(dev_now)] = 1;
+            }
         }
         p.stage_cap = uint32_t(stage);
         mark("alloc_out");
+        ev.rec(4);
         encode_write_kernel<<<unsigned(n_tiles), kBlock, stage>>>(p);
+        ev.rec(5);
         ENC_CUDA(cudaGetLastError());
         mark("write");
     }
+    ev.rec(6);
     for (int j = 0; j < k; ++j) {
         auto& c = res->chunks[size_t(j)];
         const size_t bytes = off_bytes[size_t(j)] + size_t(c.data_bytes);
@@ -744,7 +776,11 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
         c.host = h;
         ENC_CUDA(cudaMemcpyAsync(h, d_out[size_t(j)].p, bytes, cudaMemcpyDeviceToHost, nullptr));
     }
+    ev.rec(7);
     ENC_CUDA(cudaStreamSynchronize(nullptr));
+    t_enc_timings[3] = ev.ms(0, 1);
+    t_enc_timings[4] = ev.ms(6, 7);
+    if (n > 0) { t_enc_timings[0] = ev.ms(1, 2); t_enc_timings[1] = ev.ms(2, 3); t_enc_timings[2] = ev.ms(4, 5); }
     mark("download");
     if (trace) std::fprintf(stderr, "[rv trace encode] %s\n", trace_line.c_str());
     *out = res.release();

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "3",
-                          "--records", "20000", "--cpu-sample", "20000"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                          "--records", "20000"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -22,5 +22,18 @@ def test_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and d["gpu_launches"] == 0 and d["vs_baseline"] is None and d["dtype"] == "u8"
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and "sample" in cb
-    assert "workload" in d["config"] and d["config"]["records_per_step"] == 20000
+    assert cb["kind"] == "port" and 1 <= cb["cores"] <= (os.cpu_count() or 1) and cb["value"] == d["value"] and "sample" in cb
+    # both of the reference's chunk settings are timed (its own NUM_CHUNKS = 8, and 4 chunks per usable core)
+    assert [s["num_chunks"] for s in cb["settings"]] == [8, 4 * cb["cpus"]["usable"]]
+    assert cb["cpus"]["usable"] <= cb["cpus"]["affinity"]
+    # the same configuration keys as the GPU arm (the driver compares the two lines' `config`)
+    assert d["config"]["records_per_gpu"] == 20000 and d["config"]["num_chunks"] == 8 and "workload" in d["config"]
+
+
+def test_usable_cores_respects_affinity_and_quota():
+    sys.path.insert(0, ROOT)
+    import bench
+    n, aff, quota = bench.usable_cores()
+    assert 1 <= n <= aff
+    if quota is not None:
+        assert n <= max(1, int(quota + 0.999))
