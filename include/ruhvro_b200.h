@@ -48,7 +48,8 @@ typedef enum rv_status {
     RV_ERR_SCHEMA = 7,       /* schema does not parse / outside the supported subset / over a documented limit */
     RV_ERR_OVERFLOW = 8,     /* a column of one batch exceeds Arrow's i32 offsets (arrow-rs panics here) */
     RV_ERR_INVALID = 9,      /* bad argument */
-    RV_ERR_CUDA = 10         /* CUDA runtime failure (includes "no device") */
+    RV_ERR_CUDA = 10,        /* CUDA runtime failure (includes "no device") */
+    RV_ERR_VALUE = 11        /* wider subset: uuid text that is not a UUID, decimal wider than 128 bits */
 } rv_status;
 
 /* ---- schema --------------------------------------------------------------------------- */

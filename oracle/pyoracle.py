@@ -35,6 +35,7 @@ The reference (Rust) cannot be built in this image, so no ``oracle/_ref`` exists
 """
 from __future__ import annotations
 
+import copy
 import ctypes
 import json
 import os
@@ -54,7 +55,7 @@ PRIMS = {"null", "boolean", "int", "long", "float", "double", "bytes", "string"}
 
 
 class AvroSchema:
-    __slots__ = ("kind", "fullname", "doc", "aliases", "fields", "symbols", "items", "values", "variants")
+    __slots__ = ("kind", "fullname", "doc", "aliases", "fields", "symbols", "items", "values", "variants", "size", "precision", "scale")
 
     def __init__(self, kind: str, **kw: Any):
         self.kind = kind
@@ -66,6 +67,9 @@ class AvroSchema:
         self.items: Optional["AvroSchema"] = kw.get("items")
         self.values: Optional["AvroSchema"] = kw.get("values")
         self.variants: List["AvroSchema"] = kw.get("variants", [])
+        self.size: int = kw.get("size", 0)            # fixed / decimal on fixed / uuid (16)
+        self.precision: int = kw.get("precision", 0)  # decimal
+        self.scale: int = kw.get("scale", 0)
 
     def __repr__(self) -> str:  # pragma: no cover
         return f"AvroSchema({self.kind})"
@@ -87,11 +91,22 @@ def _fix_aliases(aliases, ns):
     return [a if ("." in a or not ns) else f"{ns}.{a}" for a in aliases]
 
 
-def _parse(j: Any, ns: Optional[str]) -> AvroSchema:
+# The WIDER SUBSET.  The reference's fast path rejects bytes / fixed / uuid / decimal / time-* /
+# named references (fast_decode.rs:16-17,59) and its Value-tree fallback cannot build those columns either
+# (complex.rs:414-431 `unimplemented!`), so with wide=False this module restates the reference (they are
+# "unsupported"), and with wide=True it restates what the product adds: Arrow types per schema_translate.rs:58,133-143,
+# values per the Avro specification.
+class _Names:
+    def __init__(self):
+        self.done, self.open = {}, set()
+
+
+def _parse(j: Any, ns: Optional[str], wide: bool = False, names: Optional[_Names] = None) -> AvroSchema:
+    names = names if names is not None else _Names()
     if isinstance(j, str):
-        return _prim(j, None)
+        return _prim(j, None, wide, ns, names)
     if isinstance(j, list):
-        vs = [_parse(v, ns) for v in j]
+        vs = [_parse(v, ns, wide, names) for v in j]
         if any(v.kind == "union" for v in vs):
             raise ValueError("unions may not immediately contain other unions")
         return AvroSchema("union", variants=vs)
@@ -99,60 +114,120 @@ def _parse(j: Any, ns: Optional[str]) -> AvroSchema:
         raise ValueError("invalid schema")
     t = j["type"]
     if not isinstance(t, str):
-        return _parse(t, ns)
+        return _parse(t, ns, wide, names)
     if t in ("record", "error"):
         full, rns = _name(j, ns)
+        names.open.add(full)
         # apache-avro 0.21 RecordField::parse hands the FIELD object to Parser::parse_complex: with a bare-string
         # "type", items / values / symbols / logicalType are read from the field object (ruhvro/src/serialize.rs:185
         # relies on {"name":..,"type":"array","items":..}); a bare "record" is a named look-up -> unsupported Ref
-        fields = [(f["name"],
-                   _parse(f if isinstance(f["type"], str) and f["type"] not in ("record", "error") else f["type"], rns),
-                   f.get("doc")) for f in j["fields"]]
-        return AvroSchema("record", fullname=full, doc=j.get("doc"), aliases=_fix_aliases(j.get("aliases"), rns), fields=fields)
+        fields = []
+        for f in j["fields"]:
+            ft = f["type"]
+            is_ref = isinstance(ft, str) and wide and _is_named_ref(ft, rns, names)
+            if isinstance(ft, str) and ft not in ("record", "error") and not is_ref:
+                fs = _parse(f, rns, wide, names)
+            else:
+                fs = _parse(ft, rns, wide, names)
+            fields.append((f["name"], fs, f.get("doc")))
+        r = AvroSchema("record", fullname=full, doc=j.get("doc"), aliases=_fix_aliases(j.get("aliases"), rns), fields=fields)
+        names.open.discard(full)
+        names.done[full] = r
+        return r
     if t == "enum":
         full, ens = _name(j, ns)
-        return AvroSchema("enum", fullname=full, doc=j.get("doc"), aliases=_fix_aliases(j.get("aliases"), ens), symbols=list(j["symbols"]))
+        e = AvroSchema("enum", fullname=full, doc=j.get("doc"), aliases=_fix_aliases(j.get("aliases"), ens), symbols=list(j["symbols"]))
+        names.done[full] = e
+        return e
     if t == "array":
-        return AvroSchema("array", items=_parse(j["items"], ns))
+        return AvroSchema("array", items=_parse(j["items"], ns, wide, names))
     if t == "map":
-        return AvroSchema("map", values=_parse(j["values"], ns))
-    return _prim(t, j)
+        return AvroSchema("map", values=_parse(j["values"], ns, wide, names))
+    if t == "fixed" and wide:
+        full, fns = _name(j, ns)
+        size = int(j["size"])
+        lt = j.get("logicalType")
+        if lt == "decimal":
+            f = _decimal("decimal-fixed", j, size)
+        elif lt == "duration":
+            f = AvroSchema("unsupported")
+        else:
+            f = AvroSchema("fixed", size=size)
+        f.fullname, f.doc, f.aliases = full, j.get("doc"), _fix_aliases(j.get("aliases"), fns)
+        if f.kind != "unsupported":
+            names.done[full] = f
+        return f
+    return _prim(t, j, wide, ns, names)
 
 
-def _prim(t: str, obj: Optional[dict]) -> AvroSchema:
+_BUILTIN = {"null", "boolean", "int", "long", "float", "double", "bytes", "string", "array", "map", "enum", "record", "error", "fixed"}
+
+
+def _is_named_ref(t: str, ns: Optional[str], names: _Names) -> bool:
+    if t in _BUILTIN:
+        return False
+    q = f"{ns}.{t}" if "." not in t and ns else t
+    return q in names.done or q in names.open or t in names.done or t in names.open
+
+
+def _decimal(kind: str, obj: dict, size: int) -> AvroSchema:
+    precision, scale = int(obj.get("precision", -1)), int(obj.get("scale", 0))
+    if precision < 1 or scale < 0 or scale > precision:
+        raise ValueError("decimal needs 1 <= precision and 0 <= scale <= precision")
+    if precision > 38 or (kind == "decimal-fixed" and size > 16):
+        return AvroSchema("unsupported")
+    return AvroSchema(kind, size=size, precision=precision, scale=scale)
+
+
+def _prim(t: str, obj: Optional[dict], wide: bool = False, ns: Optional[str] = None, names: Optional[_Names] = None) -> AvroSchema:
     lt = obj.get("logicalType") if obj else None
     if t == "int":
         if lt == "date":
             return AvroSchema("date")
         if lt == "time-millis":
-            return AvroSchema("unsupported")
+            return AvroSchema("time-millis" if wide else "unsupported")
         return AvroSchema("int")
     if t == "long":
         if lt == "timestamp-millis":
             return AvroSchema("timestamp-millis")
         if lt == "timestamp-micros":
             return AvroSchema("timestamp-micros")
-        if lt in ("time-micros", "timestamp-nanos", "local-timestamp-millis", "local-timestamp-micros", "local-timestamp-nanos"):
+        if lt == "time-micros":
+            return AvroSchema("time-micros" if wide else "unsupported")
+        if lt in ("timestamp-nanos", "local-timestamp-millis", "local-timestamp-micros", "local-timestamp-nanos"):
             return AvroSchema("unsupported")
         return AvroSchema("long")
     if t == "string":
-        return AvroSchema("unsupported" if lt == "uuid" else "string")
+        if lt == "uuid":
+            return AvroSchema("uuid", size=16) if wide else AvroSchema("unsupported")
+        return AvroSchema("string")
     if t in ("null", "boolean", "float", "double"):
         return AvroSchema(t)
-    return AvroSchema("unsupported")  # bytes, fixed, named Ref (fast_decode.rs:59)
+    if not wide:
+        return AvroSchema("unsupported")  # bytes, fixed, named Ref (fast_decode.rs:59)
+    if t == "bytes":
+        return _decimal("decimal-bytes", obj, 0) if lt == "decimal" else AvroSchema("bytes")
+    if names is not None:
+        for cand in ((f"{ns}.{t}" if "." not in t and ns else t), t):
+            if cand in names.open:
+                return AvroSchema("unsupported")  # recursive type
+            if cand in names.done:
+                return copy.deepcopy(names.done[cand])
+    return AvroSchema("unsupported")
 
 
-def parse_schema(schema_json: str) -> AvroSchema:
-    return _parse(json.loads(schema_json), None)
+def parse_schema(schema_json: str, wide: bool = False) -> AvroSchema:
+    return _parse(json.loads(schema_json), None, wide, _Names())
 
 
+WIDE_LEAVES = {"bytes", "fixed", "uuid", "decimal-bytes", "decimal-fixed", "time-millis", "time-micros"}
 LEAVES = {"int", "long", "float", "double", "boolean", "string", "null", "date", "timestamp-millis", "timestamp-micros", "enum"}
 
 
 def is_supported(s: AvroSchema) -> bool:
     """fast_decode.rs:38-61"""
     def inner(x: AvroSchema) -> bool:
-        if x.kind in LEAVES:
+        if x.kind in LEAVES or x.kind in WIDE_LEAVES:  # (wide kinds only exist when parsed with wide=True)
             return True
         if x.kind == "record":
             return all(inner(f[1]) for f in x.fields)
@@ -189,6 +264,14 @@ def _default_field_name(t: pa.DataType) -> str:
         return {"ms": "timestampmilli", "us": "timestampmicro"}[t.unit]
     if pa.types.is_string(t):
         return "varchar"
+    if pa.types.is_binary(t):
+        return "varbinary"
+    if pa.types.is_fixed_size_binary(t):
+        return "fixedsizebinary"
+    if pa.types.is_decimal(t):
+        return "decimal"
+    if pa.types.is_time32(t) or pa.types.is_time64(t):
+        return {"ms": "timemilli", "us": "timemicro"}[t.unit]
     if pa.types.is_map(t):
         raise NotImplementedError("Map support not implemented")  # :212 unimplemented!()
     if pa.types.is_list(t):
@@ -223,6 +306,16 @@ def _field(s: AvroSchema, name: Optional[str], nullable: bool, props: Optional[d
         t = pa.timestamp("ms")
     elif k == "timestamp-micros":
         t = pa.timestamp("us")
+    elif k == "bytes":
+        t = pa.binary()                               # schema_translate.rs:58
+    elif k in ("fixed", "uuid"):
+        t = pa.binary(s.size)                         # :133,137 FixedSizeBinary
+    elif k in ("decimal-bytes", "decimal-fixed"):
+        t = pa.decimal128(s.precision, s.scale)       # :134-136
+    elif k == "time-millis":
+        t = pa.time32("ms")                           # :139
+    elif k == "time-micros":
+        t = pa.time64("us")                           # :140
     elif k == "array":
         t = pa.list_(_field(s.items, "item", True, None))
     elif k == "map":
@@ -266,7 +359,7 @@ def _field(s: AvroSchema, name: Optional[str], nullable: bool, props: Optional[d
 def _external_props(s: AvroSchema) -> dict:
     """schema_translate.rs:222-266"""
     props = {}
-    if s.kind in ("record", "enum"):
+    if s.kind in ("record", "enum", "fixed", "decimal-fixed"):
         if s.doc is not None:
             props["avro::doc"] = s.doc
         if s.aliases is not None:
@@ -324,7 +417,35 @@ class _LazyNulls:
 
 _FIXED = {"int": ("int32", "<i", 4), "date": ("int32", "<i", 4), "long": ("int64", "<q", 8),
           "timestamp-millis": ("int64", "<q", 8), "timestamp-micros": ("int64", "<q", 8),
-          "float": ("float32", None, 4), "double": ("float64", None, 8)}
+          "float": ("float32", None, 4), "double": ("float64", None, 8),
+          "time-millis": ("int32", "<i", 4), "time-micros": ("int64", "<q", 8)}
+_RAW = ("fixed", "uuid", "decimal-bytes", "decimal-fixed")  # `width` raw bytes per row
+
+
+def _raw_width(s: AvroSchema) -> int:
+    return 16 if s.kind in ("uuid", "decimal-bytes", "decimal-fixed") else s.size
+
+
+def uuid_bytes(text: bytes) -> bytes:
+    """The 16 bytes (RFC 4122 order) of a UUID text: hyphenated 8-4-4-4-12 or 32 plain hex digits."""
+    try:
+        t = text.decode("ascii")
+    except UnicodeDecodeError:
+        raise DecodeError("value") from None
+    if len(t) == 36:
+        if any(t[i] != "-" for i in (8, 13, 18, 23)):
+            raise DecodeError("value")
+        t = t[:8] + t[9:13] + t[14:18] + t[19:23] + t[24:]
+    if len(t) != 32 or any(ch not in "0123456789abcdefABCDEF" for ch in t):
+        raise DecodeError("value")
+    return bytes.fromhex(t)
+
+
+def decimal128_le(be: bytes) -> bytes:
+    """Unscaled big-endian two's complement of any length <= 16 -> 16 bytes little-endian."""
+    if len(be) > 16:
+        raise DecodeError("value")
+    return int.from_bytes(be, "big", signed=True).to_bytes(16, "little", signed=True) if be else bytes(16)
 
 
 class _Dec:
@@ -333,7 +454,7 @@ class _Dec:
         self.s, self.k, self.nullable, self.null_first = s, s.kind, nullable, null_first
         self.values = bytearray()
         self.bools = _Bits()
-        self.offsets = bytearray(struct.pack("<i", 0)) if s.kind in ("string", "enum", "array", "map") else bytearray()
+        self.offsets = bytearray(struct.pack("<i", 0)) if s.kind in ("string", "enum", "array", "map", "bytes") else bytearray()
         self.nulls = _LazyNulls()
         self.explicit = _Bits()
         self.len = 0
@@ -409,8 +530,11 @@ def _append_null(d: _Dec):
     elif k == "boolean":
         d.bools.append(False)
         d.nulls.append(False)
-    elif k in ("string", "enum"):
+    elif k in ("string", "enum", "bytes"):
         d.offsets += struct.pack("<i", len(d.values))
+        d.nulls.append(False)
+    elif k in _RAW:
+        d.values += bytes(_raw_width(d.s))
         d.nulls.append(False)
     elif k == "null":
         d.len += 1
@@ -441,12 +565,28 @@ def _decode(d: _Dec, c: _Cur):
             _append_null(d)
             return
     k = d.k
-    if k in ("int", "date"):
+    if k in ("int", "date", "time-millis"):
         v = c.zigzag() & 0xFFFFFFFF  # `as i32` wrapping truncation
         d.values += struct.pack("<I", v)
         d.nulls.append(True)
-    elif k in ("long", "timestamp-millis", "timestamp-micros"):
+    elif k in ("long", "timestamp-millis", "timestamp-micros", "time-micros"):
         d.values += struct.pack("<q", c.zigzag())
+        d.nulls.append(True)
+    elif k == "bytes":
+        d.values += c.string()
+        d.offsets += struct.pack("<i", len(d.values))
+        d.nulls.append(True)
+    elif k == "fixed":
+        d.values += c.take(d.s.size)
+        d.nulls.append(True)
+    elif k == "uuid":
+        d.values += uuid_bytes(c.string())
+        d.nulls.append(True)
+    elif k == "decimal-bytes":
+        d.values += decimal128_le(c.string())
+        d.nulls.append(True)
+    elif k == "decimal-fixed":
+        d.values += decimal128_le(c.take(d.s.size))
         d.nulls.append(True)
     elif k == "float":
         d.values += c.take(4)
@@ -541,9 +681,13 @@ def _finish(d: _Dec) -> dict:
     if k == "boolean":
         nc, v = _lazy(d)
         return _canon("bool", d.bools.n, nc, v, [d.bools.b])
-    if k in ("string", "enum"):
+    if k in ("string", "enum", "bytes"):
         nc, v = _lazy(d)
         return _canon("utf8", len(d.offsets) // 4 - 1, nc, v, [d.offsets, d.values])
+    if k in _RAW:
+        nc, v = _lazy(d)
+        w = _raw_width(d.s)
+        return _canon("raw%d" % w, d.nulls.len, nc, v, [d.values])
     if k == "null":
         return _canon("null", d.len, d.len)
     if k == "record":
@@ -610,10 +754,16 @@ _W = {"int32": 4, "int64": 8, "float32": 4, "float64": 8}
 
 
 def _kind_of(t: pa.DataType) -> str:
-    if pa.types.is_int32(t) or pa.types.is_date32(t):
+    if pa.types.is_int32(t) or pa.types.is_date32(t) or pa.types.is_time32(t):
         return "int32"
-    if pa.types.is_int64(t) or pa.types.is_timestamp(t):
+    if pa.types.is_int64(t) or pa.types.is_timestamp(t) or pa.types.is_time64(t):
         return "int64"
+    if pa.types.is_fixed_size_binary(t):
+        return "raw%d" % t.byte_width
+    if pa.types.is_decimal(t):
+        return "raw16"
+    if pa.types.is_binary(t):
+        return "utf8"
     if pa.types.is_float32(t):
         return "float32"
     if pa.types.is_float64(t):
@@ -654,6 +804,8 @@ def canon_from_arrow(arr: pa.Array) -> dict:
     out = _canon(kind, n, arr.null_count, validity)
     if kind in _W:
         out["buffers"] = [_buf(bufs[1], n * _W[kind])]
+    elif kind.startswith("raw"):
+        out["buffers"] = [_buf(bufs[1], n * int(kind[3:]))]
     elif kind == "bool":
         out["buffers"] = [_buf(bufs[1], (n + 7) // 8)]
     elif kind == "utf8":
@@ -686,7 +838,7 @@ def canon_to_arrow(c: dict, t: pa.DataType) -> pa.Array:
     n, kind = c["length"], c["kind"]
     v = pa.py_buffer(c["validity"]) if c["validity"] is not None else None
     nc = c["null_count"]
-    if kind in _W or kind == "bool":
+    if kind in _W or kind == "bool" or kind.startswith("raw"):
         return pa.Array.from_buffers(t, n, [v, pa.py_buffer(c["buffers"][0])], null_count=nc)
     if kind == "utf8":
         return pa.Array.from_buffers(t, n, [v, pa.py_buffer(c["buffers"][0]), pa.py_buffer(c["buffers"][1])], null_count=nc)
@@ -930,8 +1082,15 @@ def encode_value(s: AvroSchema, v: Any, out: bytearray, neg_blocks: bool = False
         return
     if k == "boolean":
         out.append(1 if v else 0)
-    elif k in ("int", "long", "date", "timestamp-millis", "timestamp-micros", "enum"):
+    elif k in ("int", "long", "date", "timestamp-millis", "timestamp-micros", "enum", "time-millis", "time-micros"):
         out += zigzag_bytes(int(v))
+    elif k in ("bytes", "uuid", "decimal-bytes"):   # uuid: its text; decimal: the unscaled value's big-endian bytes
+        b = v.encode("ascii") if isinstance(v, str) else bytes(v)
+        out += zigzag_bytes(len(b))
+        out += b
+    elif k in ("fixed", "decimal-fixed"):
+        assert len(v) == s.size
+        out += bytes(v)
     elif k == "float":
         out += struct.pack("<f", v)
     elif k == "double":
@@ -986,6 +1145,27 @@ def random_value(s: AvroSchema, rng, depth: int = 0) -> Any:
         return rng.choice([0, 1, -1, 63, 64, -64, -65, 2**31 - 1, -2**31, rng.randint(-10**6, 10**6)])
     if k in ("long", "timestamp-millis", "timestamp-micros"):
         return rng.choice([0, -1, 2**63 - 1, -2**63, rng.randint(-2**40, 2**40), rng.randint(0, 200)])
+    if k == "time-millis":
+        return rng.randrange(86_400_000)
+    if k == "time-micros":
+        return rng.randrange(86_400_000_000)
+    if k == "bytes":
+        return bytes(rng.randrange(256) for _ in range(rng.choice([0, 0, 1, 5, 16, 33, rng.randint(0, 120)])))
+    if k == "fixed":
+        return bytes(rng.randrange(256) for _ in range(s.size))
+    if k == "uuid":
+        h = "%032x" % rng.getrandbits(128)
+        if rng.random() < 0.5:
+            h = h.upper()
+        return h if rng.random() < 0.2 else f"{h[:8]}-{h[8:12]}-{h[12:16]}-{h[16:20]}-{h[20:]}"
+    if k in ("decimal-bytes", "decimal-fixed"):
+        lim = 10 ** s.precision - 1
+        v = rng.choice([0, 1, -1, lim, -lim, rng.randint(-lim, lim), max(-lim, min(lim, rng.randint(-1000, 1000)))])
+        if k == "decimal-fixed":
+            return v.to_bytes(s.size, "big", signed=True) if s.size and -(1 << (8 * s.size - 1)) <= v < (1 << (8 * s.size - 1)) else bytes(s.size)
+        n = max(1, (v.bit_length() + 8) // 8)
+        n = min(16, n + rng.choice([0, 0, 1, 3]))  # writers may pad with sign bytes
+        return v.to_bytes(n, "big", signed=True) if rng.random() < 0.95 else b""
     if k == "float":
         return struct.unpack("<f", struct.pack("<f", rng.uniform(-1e6, 1e6)))[0]
     if k == "double":
@@ -1007,22 +1187,54 @@ def random_value(s: AvroSchema, rng, depth: int = 0) -> Any:
     raise NotImplementedError(k)
 
 
-def random_schema_json(rng, max_depth: int = 3) -> str:
-    """A random schema inside the supported subset (no nullable maps: SURVEY.md 8(a) hazard)."""
+def random_schema_json(rng, max_depth: int = 3, wide: bool = False) -> str:
+    """A random schema inside the supported subset (no nullable maps: SURVEY.md 8(a) hazard).  wide=True mixes in the
+    wider subset's leaves (bytes, fixed, uuid, decimal, time-*) and references to named types defined earlier."""
     counter = [0]
+    defined = []  # names of fixed / enum types a later field may reference by name
 
     def nm(prefix):
         counter[0] += 1
         return f"{prefix}{counter[0]}"
 
+    def wide_leaf():
+        r = rng.randrange(9)
+        if r == 0:
+            return "bytes"
+        if r == 1:
+            name = nm("Fx")
+            defined.append(name)
+            return {"type": "fixed", "name": name, "size": rng.choice([0, 1, 3, 4, 7, 16, 20])}
+        if r == 2:
+            return {"type": "string", "logicalType": "uuid"}
+        if r == 3:
+            p = rng.randint(1, 38)
+            return {"type": "bytes", "logicalType": "decimal", "precision": p, "scale": rng.randint(0, p)}
+        if r == 4:
+            size = rng.randint(1, 16)
+            p = rng.randint(1, min(38, max(1, int((8 * size - 1) * 0.30103))))
+            return {"type": "fixed", "name": nm("Dx"), "size": size, "logicalType": "decimal", "precision": p, "scale": rng.randint(0, p)}
+        if r == 5:
+            return {"type": "int", "logicalType": "time-millis"}
+        if r == 6:
+            return {"type": "long", "logicalType": "time-micros"}
+        if r == 7 and defined:
+            return rng.choice(defined)  # a reference by name
+        return "bytes"
+
     def leaf():
+        if wide and rng.random() < 0.5:
+            return wide_leaf()
         return rng.choice(["int", "long", "float", "double", "boolean", "string",
                            {"type": "int", "logicalType": "date"},
                            {"type": "long", "logicalType": "timestamp-millis"},
                            {"type": "long", "logicalType": "timestamp-micros"}])
 
     def enum():
-        return {"type": "enum", "name": nm("E"), "symbols": [f"S{i}" * rng.randint(1, 3) for i in range(rng.randint(1, 5))]}
+        name = nm("E")
+        if wide:
+            defined.append(name)
+        return {"type": "enum", "name": name, "symbols": [f"S{i}" * rng.randint(1, 3) for i in range(rng.randint(1, 5))]}
 
     def record(d, in_nullable):
         return {"type": "record", "name": nm("R"), "fields": [{"name": nm("f"), "type": typ(d + 1, in_nullable)} for _ in range(rng.randint(1, 4))]}

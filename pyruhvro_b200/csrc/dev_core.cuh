@@ -515,6 +515,110 @@ RV_HD void op_enum(C& c, bool valid, int slot_a, int slot_b, int slot_v, int str
     utf8_finish<MODE, D>(c, valid, len, slot_a, slot_v, cur, row);
 }
 
+// ---- the wider subset: bytes, fixed, uuid, decimal -------------------------------------
+// (time-millis / time-micros are op_i32 / op_i64; bytes is op_str.)  The reference has no code for these — its fast
+// path rejects the schemas (fast_decode.rs:16-17) and its fallback cannot build the columns (complex.rs:431) — so the
+// values follow the Avro specification and the Arrow types schema_translate.rs:58,133-143 assigns.
+
+// `n` bytes at window offset p0 -> dst (global), or zeros for a null slot.
+template <class C>
+RV_HD void store_raw(C& c, uint8_t* dst, uint32_t p0, uint32_t n, bool valid) {
+    for (uint32_t i = 0; i < n; ++i) dst[i] = valid ? uint8_t(ld_u8(c, p0 + i)) : uint8_t(0);
+}
+
+// fixed(N) -> FixedSizeBinary(N): N raw bytes.
+template <int MODE, int D, class C>
+RV_HD void op_fixed(C& c, bool valid, int n_, int slot_a, int slot_v, uint32_t row) {
+    const uint32_t n = uint32_t(n_), p0 = c.pos;
+    if (valid) {
+        if (MODE == WM_COUNT && (C::kShared ? c.pos + n > c.end : c.end - c.pos < n)) { fail(c, E_EOF); valid = false; }
+        else c.pos += n;
+    }
+    if (MODE == WM_EMIT) {
+        if (may_store<D>(c)) store_raw(c, static_cast<uint8_t*>(buf_ptr(c, slot_a)) + size_t(row) * n, p0, n, valid);
+        if (slot_v >= 0) put_bit<D>(c, slot_v, row, valid);
+    }
+}
+
+RV_HD int hex_val(uint32_t ch) {
+    if (ch >= '0' && ch <= '9') return int(ch - '0');
+    ch |= 0x20u;
+    if (ch >= 'a' && ch <= 'f') return int(ch - 'a' + 10);
+    return -1;
+}
+
+// uuid (a string on the wire) -> FixedSizeBinary(16), RFC 4122 byte order.  Accepted texts: the hyphenated form
+// (8-4-4-4-12, 36 characters) and the plain 32 hex digits.
+template <int MODE, int D, class C>
+RV_HD void op_uuid(C& c, bool valid, int slot_a, int slot_v, uint32_t row) {
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (valid) {
+        uint32_t len = 0;
+        if (!rd_len<MODE == WM_COUNT>(c, len)) { valid = false; }
+        else if (MODE == WM_COUNT && (C::kShared ? c.err != 0 : false)) { /* not plain: the precise flavour decides */ }
+        else if (len != 36u && len != 32u) { if (MODE == WM_COUNT) { fail(c, E_VALUE); if (!C::kShared) valid = false; } }
+        else {
+            const bool hyph = len == 36u;
+            uint32_t p = c.pos;
+            bool ok = true;
+            for (int i = 0; i < 16; ++i) {
+                if (hyph && (i == 4 || i == 6 || i == 8 || i == 10)) { ok = ok && ld_u8(c, p) == uint32_t('-'); ++p; }
+                const int hi = hex_val(ld_u8(c, p)), lo = hex_val(ld_u8(c, p + 1));
+                p += 2;
+                ok = ok && hi >= 0 && lo >= 0;
+                w[i >> 2] |= uint32_t(((hi & 15) << 4) | (lo & 15)) << ((i & 3) * 8);
+            }
+            if (MODE == WM_COUNT && !ok) { fail(c, E_VALUE); if (!C::kShared) valid = false; }
+            else c.pos += len;
+        }
+    }
+    if (MODE == WM_EMIT) {
+        if (may_store<D>(c)) {
+            uint32_t* dst = static_cast<uint32_t*>(buf_ptr(c, slot_a)) + size_t(row) * 4;
+            for (int i = 0; i < 4; ++i) dst[i] = valid ? w[i] : 0u;
+        }
+        if (slot_v >= 0) put_bit<D>(c, slot_v, row, valid);
+    }
+}
+
+// decimal -> Decimal128: `fixed_n` < 0: bytes (varint length first), else fixed(N).  The payload is the unscaled value,
+// big-endian two's complement; it is sign-extended into the 16-byte little-endian Arrow value.  More than 16 bytes
+// cannot be represented: E_VALUE.
+template <int MODE, int D, class C>
+RV_HD void op_decimal(C& c, bool valid, int fixed_n, int slot_a, int slot_v, uint32_t row) {
+    uint64_t lo = 0, hi = 0;
+    if (valid) {
+        uint32_t len = 0;
+        bool ok = true;
+        if (fixed_n < 0) {
+            ok = rd_len<MODE == WM_COUNT>(c, len);
+            if (ok && MODE == WM_COUNT && len > 16u) { fail(c, E_VALUE); ok = C::kShared; len = 0; }
+        } else {
+            len = uint32_t(fixed_n);
+            if (MODE == WM_COUNT && (C::kShared ? c.pos + len > c.end : c.end - c.pos < len)) { fail(c, E_EOF); ok = false; }
+        }
+        if (!ok) valid = false;
+        else {
+            if (MODE == WM_EMIT && len > 0) {
+                lo = hi = (ld_u8(c, c.pos) & 0x80u) ? ~0ull : 0ull;
+                for (uint32_t i = 0; i < len; ++i) {
+                    hi = (hi << 8) | (lo >> 56);
+                    lo = (lo << 8) | uint64_t(ld_u8(c, c.pos + i));
+                }
+            }
+            c.pos += len;
+        }
+    }
+    if (MODE == WM_EMIT) {
+        if (may_store<D>(c)) {
+            uint64_t* dst = static_cast<uint64_t*>(buf_ptr(c, slot_a)) + size_t(row) * 2;
+            dst[0] = lo;
+            dst[1] = hi;
+        }
+        if (slot_v >= 0) put_bit<D>(c, slot_v, row, valid);
+    }
+}
+
 // ---- containers -------------------------------------------------------------------------------
 // N-variant union head (UnionDecoder::decode / append_null :643-668): returns the selected variant
 // (-1: the union itself is absent -> every child appends null, type_id 0).

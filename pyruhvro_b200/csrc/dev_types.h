@@ -85,7 +85,8 @@ enum ErrCode : uint32_t {
     E_BRANCH = 5,    // "invalid union branch index" / "out of range" (:591,646)
     E_ENUM = 6,      // "enum index out of range" (:575)
     E_SCHEMA = 7,
-    E_OVERFLOW = 8   // i32 Arrow offset overflow (arrow-rs panics; reported as an error)
+    E_OVERFLOW = 8,  // i32 Arrow offset overflow (arrow-rs panics; reported as an error)
+    E_VALUE = 11     // wider subset: a value its logical type cannot hold (uuid text that is not a UUID, decimal wider than 128 bits)
 };
 
 #ifndef RV_KBLOCK

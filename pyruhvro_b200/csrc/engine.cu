@@ -505,6 +505,7 @@ const char* err_text(uint32_t code) {
         case E_BRANCH: return "invalid union branch index";
         case E_ENUM: return "enum index out of range";
         case E_OVERFLOW: return "Arrow i32 offset overflow (or malformed input offsets)";
+        case E_VALUE: return "value does not fit its logical type (uuid text / decimal wider than 128 bits)";
         default: return "decode error";
     }
 }

@@ -23,7 +23,7 @@ struct Builder {
     int add_slot(SlotRole role, int node, int space, int stream) {
         if (p.slots.size() >= 32000) throw std::runtime_error("schema too wide: too many Arrow buffers");
         Slot s;
-        s.role = role; s.node = node; s.space = space; s.stream = stream;
+        s.role = role; s.node = node; s.space = space; s.stream = stream; s.width = 0;
         s.zero_init = (role == SlotRole::Validity || role == SlotRole::Bits) && space > 0;
         p.slots.push_back(s);
         int id = int(p.slots.size()) - 1;
@@ -132,9 +132,21 @@ struct Builder {
             p.arrays[arr].slot_b = sb;
             return std::make_pair(id, arr);
         };
+        auto wide = [&](NodeKind nk, int width, int aux) {  // `width` raw bytes per row
+            auto [id, arr] = leaf(nk, SlotRole::ValuesW);
+            p.slots[size_t(p.nodes[id].slot_a)].width = width;
+            p.nodes[id].aux = aux;
+            p.arrays[arr].width = width;
+            return arr;
+        };
         switch (s.k) {
-            case AK::Int: case AK::Date: return leaf(NK_I32, SlotRole::Values32).second;
-            case AK::Long: case AK::TsMillis: case AK::TsMicros: return leaf(NK_I64, SlotRole::Values64).second;
+            case AK::Int: case AK::Date: case AK::TimeMillis: return leaf(NK_I32, SlotRole::Values32).second;
+            case AK::Long: case AK::TsMillis: case AK::TsMicros: case AK::TimeMicros: return leaf(NK_I64, SlotRole::Values64).second;
+            case AK::Bytes: return utf8(NK_BYTES).second;
+            case AK::Fixed: return wide(NK_FIXED, s.size, s.size);
+            case AK::Uuid: return wide(NK_UUID, 16, 16);
+            case AK::DecimalBytes: return wide(NK_DEC_BYTES, 16, 0);
+            case AK::DecimalFixed: return wide(NK_DEC_FIXED, 16, s.size);
             case AK::Float: return leaf(NK_F32, SlotRole::Values32).second;
             case AK::Double: return leaf(NK_F64, SlotRole::Values64).second;
             case AK::Bool: return leaf(NK_BOOL, SlotRole::Bits).second;

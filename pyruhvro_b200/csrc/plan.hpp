@@ -23,7 +23,7 @@
 namespace rv {
 
 // ---- host-side description ----------------------------------------------------
-enum class SlotRole : uint8_t { Validity, Bits, Values32, Values64, Offsets, Data, TypeIds };
+enum class SlotRole : uint8_t { Validity, Bits, Values32, Values64, Offsets, Data, TypeIds, ValuesW };  // ValuesW: `width` bytes per row
 
 struct Slot {
     SlotRole role;
@@ -31,6 +31,7 @@ struct Slot {
     int space;     // row space whose row count sizes this buffer (Data: unused)
     int stream;    // Data: the byte stream that sizes it
     bool zero_init;  // written with atomicOr (bit buffers in spaces > 0): must start zeroed
+    int width = 0;   // ValuesW: bytes per row (FixedSizeBinary(N): N, Decimal128: 16)
 };
 
 struct Stream {
@@ -42,6 +43,7 @@ struct Stream {
 // One Arrow array of the output tree (what finish() returns, fast_decode.rs:536-567).
 struct OutArray {
     AT type;
+    int width = 0;     // FixedSizeBinary
     int node;          // DNode that owns the buffers (-1 for a map's synthetic entries struct)
     int space;         // row space giving its length
     bool always_validity;  // nullable record/list/map: bitmap always exported (:629,739,790)

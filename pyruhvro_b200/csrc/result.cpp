@@ -61,7 +61,7 @@ struct Exporter {
             case AT::SparseUnion: p->buffers = {buf(a.slot_a)}; nulls = 0; break;
             case AT::Struct: p->buffers = {validity}; break;
             case AT::List: case AT::Map: p->buffers = {validity, buf(a.slot_a)}; break;
-            case AT::Utf8: p->buffers = {validity, buf(a.slot_a), buf(a.slot_b)}; break;
+            case AT::Utf8: case AT::Binary: p->buffers = {validity, buf(a.slot_a), buf(a.slot_b)}; break;
             default: p->buffers = {validity, buf(a.slot_a)}; break;
         }
         p->child_storage.resize(a.children.size());
@@ -111,6 +111,7 @@ Layout compute_layout(const Plan& plan, int64_t n, int k, const unsigned long lo
                         logical = (rows + 7) / 8; alloc = size_t((rows + 31) / 32) * 4; break;  // written as 32-bit words
                     case SlotRole::Values32: logical = rows * 4; alloc = size_t(logical); break;
                     case SlotRole::Values64: logical = rows * 8; alloc = size_t(logical); break;
+                    case SlotRole::ValuesW: logical = rows * slot.width; alloc = size_t(logical); break;
                     case SlotRole::Offsets: logical = (rows + 1) * 4; alloc = size_t(logical); break;
                     case SlotRole::TypeIds: logical = rows; alloc = size_t(logical); break;
                     case SlotRole::Data:

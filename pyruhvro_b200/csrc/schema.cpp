@@ -3,6 +3,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <set>
 #include <stdexcept>
 
@@ -23,6 +24,28 @@ std::unique_ptr<AvroNode> unsupported(const std::string& what) {
     n->what = what;
     return n;
 }
+
+std::unique_ptr<AvroNode> clone_node(const AvroNode& n) {
+    auto c = std::make_unique<AvroNode>();
+    c->k = n.k; c->fullname = n.fullname; c->has_doc = n.has_doc; c->doc = n.doc; c->has_aliases = n.has_aliases;
+    c->aliases = n.aliases; c->symbols = n.symbols; c->what = n.what; c->size = n.size; c->precision = n.precision; c->scale = n.scale;
+    for (auto& f : n.fields) {
+        AvroField cf;
+        cf.name = f.name; cf.has_doc = f.has_doc; cf.doc = f.doc;
+        cf.type = clone_node(*f.type);
+        c->fields.push_back(std::move(cf));
+    }
+    for (auto& s : n.sub) c->sub.push_back(clone_node(*s));
+    return c;
+}
+
+// Named types seen so far (record / enum / fixed), for references by name (apache_avro Schema::Ref): a reference
+// decodes exactly like the definition it names, so it is replaced by a copy of it.  A name that is still being
+// defined (a recursive type) has no finite Arrow type and stays unsupported.
+struct Names {
+    std::map<std::string, const AvroNode*> done;
+    std::set<std::string> open;
+};
 
 // Name resolution as apache-avro does it: a dotted name carries its own namespace,
 // otherwise the "namespace" attribute, otherwise the enclosing namespace.
@@ -55,7 +78,24 @@ void read_doc_aliases(const Json& j, const std::string& ns, AvroNode* n) {
     }
 }
 
-std::unique_ptr<AvroNode> primitive(const std::string& t, const Json* obj) {
+int json_int(const Json* j, int dflt) {
+    if (!j) return dflt;
+    if (j->kind == Json::Number) return int(std::strtol(j->str.c_str(), nullptr, 10));
+    return dflt;
+}
+
+std::unique_ptr<AvroNode> decimal_of(AK k, const Json* obj, int size) {
+    const int precision = json_int(obj ? obj->find("precision") : nullptr, -1);
+    const int scale = json_int(obj ? obj->find("scale") : nullptr, 0);
+    if (precision < 1 || scale < 0 || scale > precision) bad("decimal needs 1 <= precision and 0 <= scale <= precision");
+    if (precision > 38) return unsupported("decimal with precision above 38 (Decimal128)");
+    if (k == AK::DecimalFixed && size > 16) return unsupported("decimal on a fixed wider than 16 bytes");
+    auto n = mk(k);
+    n->precision = precision; n->scale = scale; n->size = size;
+    return n;
+}
+
+std::unique_ptr<AvroNode> primitive(const std::string& t, const Json* obj, const std::string& ns, Names& names) {
     std::string lt;
     if (obj)
         if (const Json* l = obj->find("logicalType"); l && l->is_string()) lt = l->str;
@@ -65,43 +105,58 @@ std::unique_ptr<AvroNode> primitive(const std::string& t, const Json* obj) {
     if (t == "double") return mk(AK::Double);
     if (t == "int") {
         if (lt == "date") return mk(AK::Date);
-        if (lt == "time-millis") return unsupported("time-millis");
+        if (lt == "time-millis") return mk(AK::TimeMillis);
         return mk(AK::Int);  // unknown logical types degrade to the base type
     }
     if (t == "long") {
         if (lt == "timestamp-millis") return mk(AK::TsMillis);
         if (lt == "timestamp-micros") return mk(AK::TsMicros);
-        if (lt == "time-micros" || lt == "timestamp-nanos" || lt == "local-timestamp-millis" ||
-            lt == "local-timestamp-micros" || lt == "local-timestamp-nanos")
+        if (lt == "time-micros") return mk(AK::TimeMicros);
+        if (lt == "timestamp-nanos" || lt == "local-timestamp-millis" || lt == "local-timestamp-micros" || lt == "local-timestamp-nanos")
             return unsupported(lt);
         return mk(AK::Long);
     }
     if (t == "string") {
-        if (lt == "uuid") return unsupported("uuid");
+        if (lt == "uuid") return mk(AK::Uuid);
         return mk(AK::String);
     }
-    if (t == "bytes") return unsupported(lt == "decimal" ? "decimal" : "bytes");
-    if (t == "fixed") return unsupported(lt.empty() ? "fixed" : lt);
-    return unsupported("named type reference \"" + t + "\"");  // Schema::Ref (fast_decode.rs:59)
+    if (t == "bytes") {
+        if (lt == "decimal") return decimal_of(AK::DecimalBytes, obj, 0);
+        return mk(AK::Bytes);
+    }
+    // a reference to a named type defined earlier in the document (Schema::Ref)
+    for (const std::string& cand : {t.find('.') == std::string::npos && !ns.empty() ? ns + "." + t : t, t}) {
+        if (names.open.count(cand)) return unsupported("recursive reference to named type \"" + cand + "\"");
+        auto it = names.done.find(cand);
+        if (it != names.done.end()) return clone_node(*it->second);
+    }
+    return unsupported("reference to unknown named type \"" + t + "\"");
 }
 
 // Key used for the "unions may not contain duplicate types" rule.
 std::string union_key(const AvroNode& n) {
     switch (n.k) {
-        case AK::Record: case AK::Enum: return "named:" + n.fullname;
+        case AK::Record: case AK::Enum: case AK::Fixed: case AK::DecimalFixed: return "named:" + n.fullname;
         case AK::Unsupported: return "unsupported:" + n.what;
         default: return "kind:" + std::to_string(int(n.k));
     }
 }
 
-std::unique_ptr<AvroNode> parse_node(const Json& j, const std::string& ns, int depth) {
+bool is_named_ref(const std::string& t, const std::string& ns, const Names& names) {
+    static const std::set<std::string> builtin = {"null", "boolean", "int", "long", "float", "double", "bytes", "string", "array", "map", "enum", "record", "error", "fixed"};
+    if (builtin.count(t)) return false;
+    const std::string q = t.find('.') == std::string::npos && !ns.empty() ? ns + "." + t : t;
+    return names.done.count(q) || names.open.count(q) || names.done.count(t) || names.open.count(t);
+}
+
+std::unique_ptr<AvroNode> parse_node(const Json& j, const std::string& ns, int depth, Names& names) {
     if (depth > 64) bad("schema nesting too deep");
-    if (j.kind == Json::String) return primitive(j.str, nullptr);
+    if (j.kind == Json::String) return primitive(j.str, nullptr, ns, names);
     if (j.kind == Json::Array) {
         auto u = mk(AK::Union);
         std::set<std::string> seen;
         for (auto& v : j.arr) {
-            auto c = parse_node(v, ns, depth + 1);
+            auto c = parse_node(v, ns, depth + 1, names);
             if (c->k == AK::Union) bad("unions may not immediately contain other unions");
             if (!seen.insert(union_key(*c)).second) bad("unions cannot contain duplicate types");
             u->sub.push_back(std::move(c));
@@ -112,13 +167,14 @@ std::unique_ptr<AvroNode> parse_node(const Json& j, const std::string& ns, int d
     if (j.kind != Json::Object) bad("a schema must be a string, array or object");
     const Json* t = j.find("type");
     if (!t) bad("object schema without \"type\"");
-    if (!t->is_string()) return parse_node(*t, ns, depth + 1);
+    if (!t->is_string()) return parse_node(*t, ns, depth + 1, names);
     const std::string& ts = t->str;
     if (ts == "record" || ts == "error") {
         auto r = mk(AK::Record);
         std::string rns;
         resolve_name(j, ns, &r->fullname, &rns);
         read_doc_aliases(j, rns, r.get());
+        names.open.insert(r->fullname);
         const Json* fs = j.find("fields");
         if (!fs || fs->kind != Json::Array) bad("record without a \"fields\" array");
         for (auto& fj : fs->arr) {
@@ -134,11 +190,15 @@ std::unique_ptr<AvroNode> parse_node(const Json& j, const std::string& ns, int d
             // is an array (the reference relies on it: ruhvro/src/serialize.rs:185-186), an "enum" takes the field's
             // name and "symbols", and a field-level "logicalType" annotates a primitive.  A bare "record" there is a
             // look-up of an already defined type by the field's name: a named reference, which the gate rejects.
-            if (ft->is_string() && ft->str != "record" && ft->str != "error") f.type = parse_node(fj, rns, depth + 1);
-            else f.type = parse_node(*ft, rns, depth + 1);
+            if (ft->is_string() && ft->str != "record" && ft->str != "error" && ft->str != "fixed" && !is_named_ref(ft->str, rns, names))
+                f.type = parse_node(fj, rns, depth + 1, names);
+            else if (ft->is_string() && ft->str == "fixed") f.type = parse_node(fj, rns, depth + 1, names);  // {"name":..,"type":"fixed","size":..}: the field object is the fixed
+            else f.type = parse_node(*ft, rns, depth + 1, names);
             if (const Json* d = fj.find("doc"); d && d->is_string()) { f.has_doc = true; f.doc = d->str; }
             r->fields.push_back(std::move(f));
         }
+        names.open.erase(r->fullname);
+        names.done[r->fullname] = r.get();
         return r;
     }
     if (ts == "enum") {
@@ -152,22 +212,40 @@ std::unique_ptr<AvroNode> parse_node(const Json& j, const std::string& ns, int d
             if (!s.is_string()) bad("enum symbols must be strings");
             e->symbols.push_back(s.str);
         }
+        names.done[e->fullname] = e.get();
         return e;
+    }
+    if (ts == "fixed") {
+        std::string fullname, fns;
+        resolve_name(j, ns, &fullname, &fns);
+        const int size = json_int(j.find("size"), -1);
+        if (size < 0) bad("fixed without a non-negative \"size\"");
+        std::string lt;
+        if (const Json* l = j.find("logicalType"); l && l->is_string()) lt = l->str;
+        std::unique_ptr<AvroNode> f;
+        if (lt == "decimal") f = decimal_of(AK::DecimalFixed, &j, size);
+        else if (lt == "duration") f = unsupported("duration");
+        else { f = mk(AK::Fixed); f->size = size; }
+        f->fullname = fullname;
+        read_doc_aliases(j, fns, f.get());
+        if (f->k != AK::Unsupported) names.done[fullname] = f.get();
+        return f;
     }
     if (ts == "array" || ts == "map") {
         auto a = mk(ts == "array" ? AK::Array : AK::Map);
         const Json* it = j.find(ts == "array" ? "items" : "values");
         if (!it) bad(ts == "array" ? "array without \"items\"" : "map without \"values\"");
-        a->sub.push_back(parse_node(*it, ns, depth + 1));
+        a->sub.push_back(parse_node(*it, ns, depth + 1, names));
         return a;
     }
-    return primitive(ts, &j);
+    return primitive(ts, &j, ns, names);
 }
 
 bool supported_inner(const AvroNode& n, std::string* why) {
     switch (n.k) {
         case AK::Int: case AK::Long: case AK::Float: case AK::Double: case AK::Bool: case AK::String: case AK::Null:
         case AK::Date: case AK::TsMillis: case AK::TsMicros: case AK::Enum:
+        case AK::Bytes: case AK::Fixed: case AK::DecimalBytes: case AK::DecimalFixed: case AK::Uuid: case AK::TimeMillis: case AK::TimeMicros:
             return true;
         case AK::Record:
             for (auto& f : n.fields)
@@ -197,6 +275,11 @@ const char* default_field_name(AT t) {  // :155-220
         case AT::TsMs: return "timestampmilli";
         case AT::TsUs: return "timestampmicro";
         case AT::Utf8: return "varchar";
+        case AT::Binary: return "varbinary";
+        case AT::FixedSizeBinary: return "fixedsizebinary";
+        case AT::Decimal128: return "decimal";
+        case AT::Time32Ms: return "timemilli";
+        case AT::Time64Us: return "timemicro";
         case AT::List: return "list";
         case AT::Struct: return "struct";
         case AT::SparseUnion: return "union";
@@ -221,6 +304,13 @@ ArrowField to_field(const AvroNode& s, const std::string* name, bool nullable, c
         case AK::Date: f.type = AT::Date32; break;
         case AK::TsMillis: f.type = AT::TsMs; break;
         case AK::TsMicros: f.type = AT::TsUs; break;
+        case AK::Bytes: f.type = AT::Binary; break;                                        // :58
+        case AK::Fixed: f.type = AT::FixedSizeBinary; f.width = s.size; break;             // :133
+        case AK::Uuid: f.type = AT::FixedSizeBinary; f.width = 16; break;                  // :137
+        case AK::DecimalBytes: case AK::DecimalFixed:                                      // :134-136
+            f.type = AT::Decimal128; f.precision = s.precision; f.scale = s.scale; break;
+        case AK::TimeMillis: f.type = AT::Time32Ms; break;                                 // :139
+        case AK::TimeMicros: f.type = AT::Time64Us; break;                                 // :140
         case AK::Array: {  // :60-65
             f.type = AT::List;
             std::string item = "item";
@@ -252,6 +342,7 @@ ArrowField to_field(const AvroNode& s, const std::string* name, bool nullable, c
                 ArrowField in = to_field(*inner, nullptr, true, nullptr);
                 f.type = in.type;
                 f.children = std::move(in.children);
+                f.width = in.width; f.precision = in.precision; f.scale = in.scale;
             } else {
                 if (has_null) nullable = true;
                 if (s.sub.size() > 127) throw std::runtime_error("union with more than 127 variants (Arrow type ids are i8)");
@@ -286,7 +377,7 @@ ArrowField to_field(const AvroNode& s, const std::string* name, bool nullable, c
 
 Props external_props(const AvroNode& s) {  // :222-266
     Props p;
-    if (s.k == AK::Record || s.k == AK::Enum) {
+    if (s.k == AK::Record || s.k == AK::Enum || s.k == AK::Fixed || s.k == AK::DecimalFixed) {
         if (s.has_doc) p.emplace_back("avro::doc", s.doc);
         if (s.has_aliases) {
             std::string joined = "[";
@@ -326,6 +417,11 @@ std::string format_of(const ArrowField& f) {
         case AT::Float32: return "f";
         case AT::Float64: return "g";
         case AT::Utf8: return "u";
+        case AT::Binary: return "z";
+        case AT::FixedSizeBinary: return "w:" + std::to_string(f.width);
+        case AT::Decimal128: return "d:" + std::to_string(f.precision) + "," + std::to_string(f.scale);
+        case AT::Time32Ms: return "ttm";
+        case AT::Time64Us: return "ttu";
         case AT::Date32: return "tdD";
         case AT::TsMs: return "tsm:";
         case AT::TsUs: return "tsu:";
@@ -379,7 +475,8 @@ void fill_schema(const ArrowField& f, ArrowSchema* out) {
 std::unique_ptr<AvroNode> parse_avro_schema(const char* json, size_t len) {
     JsonReader rd(json, len);
     Json doc = rd.parse_document();
-    return parse_node(doc, std::string(), 0);
+    Names names;
+    return parse_node(doc, std::string(), 0, names);
 }
 
 bool is_supported(const AvroNode& top, std::string* why) {

@@ -17,7 +17,11 @@ namespace rv {
 
 enum class AK : uint8_t {
     Null, Bool, Int, Long, Float, Double, String, Date, TsMillis, TsMicros, Enum, Record, Union, Array, Map,
-    Unsupported  // bytes, fixed, decimal, uuid, duration, time-*, local-timestamp-*, named Ref
+    // the wider subset: schemas the reference's fast path rejects (fast_decode.rs:16-17,59) and
+    // its Value-tree fallback cannot build either (complex.rs:414-431 `unimplemented!`); Arrow types per
+    // schema_translate.rs:58,133-143, values per the Avro specification
+    Bytes, Fixed, DecimalBytes, DecimalFixed, Uuid, TimeMillis, TimeMicros,
+    Unsupported  // duration, local-timestamp-*, timestamp-nanos, decimals beyond 128 bits, recursive named references
 };
 
 struct AvroNode;
@@ -38,6 +42,8 @@ struct AvroNode {
     std::vector<std::string> symbols;  // enum
     std::vector<std::unique_ptr<AvroNode>> sub;  // union variants; array: [items]; map: [values]
     std::string what;                  // Unsupported: which construct
+    int32_t size = 0;                  // fixed / decimal on fixed: bytes
+    int32_t precision = 0, scale = 0;  // decimal
 };
 
 // Throws std::runtime_error on malformed documents.
@@ -46,7 +52,8 @@ std::unique_ptr<AvroNode> parse_avro_schema(const char* json, size_t len);
 // fast_decode.rs:38-61.  `why` receives the first offending construct.
 bool is_supported(const AvroNode& top, std::string* why);
 
-enum class AT : uint8_t { Null, Bool, Int32, Int64, Float32, Float64, Utf8, Date32, TsMs, TsUs, Struct, List, Map, SparseUnion };
+enum class AT : uint8_t { Null, Bool, Int32, Int64, Float32, Float64, Utf8, Date32, TsMs, TsUs, Struct, List, Map, SparseUnion,
+                          Binary, FixedSizeBinary, Decimal128, Time32Ms, Time64Us };
 
 struct ArrowField {
     std::string name;
@@ -54,6 +61,8 @@ struct ArrowField {
     bool nullable = false;
     std::vector<std::pair<std::string, std::string>> metadata;
     std::vector<ArrowField> children;  // struct fields / union variants / list: [item] / map: [entries{keys,values}]
+    int32_t width = 0;                 // FixedSizeBinary
+    int32_t precision = 0, scale = 0;  // Decimal128
 };
 
 // schema_translate.rs:19-37: one ArrowField per top-level record field.

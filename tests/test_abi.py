@@ -85,19 +85,33 @@ def test_metadata_doc_and_aliases():
     assert got.field("e").metadata is None  # enum fields never carry metadata (schema_translate.rs:131)
 
 
-@pytest.mark.parametrize("bad", ["bytes", {"type": "fixed", "name": "F", "size": 4}, {"type": "string", "logicalType": "uuid"},
-                                 {"type": "int", "logicalType": "time-millis"}, {"type": "long", "logicalType": "time-micros"},
-                                 {"type": "bytes", "logicalType": "decimal", "precision": 4, "scale": 2}])
-def test_gate_rejects_what_the_reference_rejects(bad, coracle):
-    sj = json.dumps({"type": "record", "name": "T", "fields": [{"name": "x", "type": bad}, {"name": "y", "type": "int"}]})
-    assert not pr.Schema(sj).is_supported                 # fast_decode.rs:59
+@pytest.mark.parametrize("wide", ["bytes", {"type": "fixed", "name": "F", "size": 4}, {"type": "string", "logicalType": "uuid"},
+                                  {"type": "int", "logicalType": "time-millis"}, {"type": "long", "logicalType": "time-micros"},
+                                  {"type": "bytes", "logicalType": "decimal", "precision": 4, "scale": 2}])
+def test_gate_is_wider_than_the_references_fast_path(wide, coracle):
+    """These types make the reference leave its fast path (fast_decode.rs:16-17,59; both restatements agree) and its
+    fallback cannot build them; the product decodes them (tests/test_wide_types.py)."""
+    sj = json.dumps({"type": "record", "name": "T", "fields": [{"name": "x", "type": wide}, {"name": "y", "type": "int"}]})
     assert not coracle.is_supported(sj) and not po.is_supported(po.parse_schema(sj))
+    assert pr.Schema(sj).is_supported and po.is_supported(po.parse_schema(sj, wide=True))
 
 
-def test_gate_rejects_named_refs_and_non_records(coracle):
+@pytest.mark.parametrize("bad", [{"type": "fixed", "name": "D", "size": 12, "logicalType": "duration"},
+                                 {"type": "long", "logicalType": "local-timestamp-micros"},
+                                 {"type": "bytes", "logicalType": "decimal", "precision": 60, "scale": 2}])
+def test_gate_still_rejects(bad):
+    sj = json.dumps({"type": "record", "name": "T", "fields": [{"name": "x", "type": bad}, {"name": "y", "type": "int"}]})
+    assert not pr.Schema(sj).is_supported
+
+
+def test_gate_named_refs_and_non_records(coracle):
     sj = json.dumps({"type": "record", "name": "T", "fields": [
         {"name": "a", "type": {"type": "record", "name": "A", "fields": [{"name": "x", "type": "int"}]}}, {"name": "b", "type": "A"}]})
-    assert not pr.Schema(sj).is_supported
+    assert not coracle.is_supported(sj)                   # Schema::Ref leaves the reference's fast path (fast_decode.rs:59)
+    assert pr.Schema(sj).is_supported                     # here a reference decodes like the definition it names
+    assert pr.Schema(sj).arrow_schema.field("b").type == pr.Schema(sj).arrow_schema.field("a").type
+    rec = json.dumps({"type": "record", "name": "L", "fields": [{"name": "next", "type": ["null", "L"]}]})
+    assert not pr.Schema(rec).is_supported                # a recursive type has no finite Arrow type
     assert not pr.Schema('"string"').is_supported
     assert not pr.Schema('{"type":"array","items":"int"}').is_supported
 

@@ -242,7 +242,7 @@ def test_error_surface():
     with pytest.raises(TypeError):
         pr.deserialize_array([b"ok", "not-bytes"], G.G1_SCHEMA)
     with pytest.raises(ValueError):
-        pr.deserialize_array([b""], '{"type":"record","name":"B","fields":[{"name":"x","type":"bytes"}]}')  # no CPU fallback
+        pr.deserialize_array([b""], '{"type":"record","name":"B","fields":[{"name":"x","type":{"type":"long","logicalType":"local-timestamp-millis"}}]}')  # no CPU fallback
     with pytest.raises(ValueError):
         pr.deserialize_array([b""], "{not json")
 

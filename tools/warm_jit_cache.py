@@ -25,6 +25,11 @@ def schemas():
                '{"name":"m","type":{"type":"map","values":{"type":"array","items":{"type":"array","items":["null","string"]}}}}]}')
     out.append('{"type":"record","name":"C","fields":[{"name":"id","type":"long"},{"name":"s","type":["null","string"]},'
                '{"name":"xs","type":{"type":"array","items":"int"}}]}')
+    from tests.parity import gen_case_wide
+    from tests.test_wide_types import ALL_WIDE
+    out.append(ALL_WIDE)
+    out += [gen_case_wide(seed, n=1)[0] for seed in range(30) if seed % 3]
+    out.append('{"type":"record","name":"R","fields":[{"name":"id","type":"long"},{"name":"u","type":{"type":"string","logicalType":"uuid"}}]}')
     return list(dict.fromkeys(out))
 
 
