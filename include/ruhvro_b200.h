@@ -129,10 +129,32 @@ void rv_encoded_free(rv_encoded* r);
  * [3] upload of the Arrow buffers, [4] download of the datums.  Returns how many entries were written. */
 int rv_last_encode_timings(float* out_ms, int cap);
 
-/* ---- multi-GPU: fix-ups for gathering shard-local batches into ONE RecordBatch -------------------------
+/* ---- multi-GPU: gathering shard-local batches into single RecordBatches ---------------------------------------------
  * Records shard by message; each rank decodes its contiguous range (exactly the reference's per-chunk batches,
- * deserialize.rs:57-68).  When a single batch is wanted the ranks all-gather every Arrow buffer (NCCL) and fix
- * them up on the device with these two kernels (pyruhvro_b200/distributed.py drives it). */
+ * deserialize.rs:57-68).  When one batch over all rows is wanted (BASELINE.json configs[4]) the ranks exchange
+ * rv_gather_meta_len() int64 counts each, every rank computes the same plan from them (rv_gather_plan: consecutive
+ * ranks are grouped into as few batches as Arrow's i32 offsets allow), the leader of each group allocates the gathered
+ * arena (rv_gather_alloc) and shares it with its group (rv_ipc_export / rv_ipc_open), and every member PUSHES its
+ * buffers into it with one kernel (rv_gather_push: peer stores over NVLink, offsets rebased and bitmaps bit-shifted on
+ * the way).  After a barrier the leader wraps the arena as an ordinary device-resident result (rv_gather_finish).
+ * pyruhvro_b200/distributed.py drives this over torch.distributed. */
+typedef struct rv_gather rv_gather;
+int64_t rv_gather_meta_len(const rv_schema* s);
+rv_status rv_result_gather_meta(const rv_result* r, int64_t batch, int64_t* out, int64_t cap);
+rv_status rv_gather_plan(const rv_schema* s, const int64_t* metas /* [world][meta_len] */, int world, rv_gather** out);
+int rv_gather_num_groups(const rv_gather* g);
+int rv_gather_group_of_rank(const rv_gather* g, int rank);
+/* out[0] leader rank, out[1] ranks in the group, out[2] arena bytes, out[3] rows of the gathered batch, out[4] bytes pushed by non-leaders */
+rv_status rv_gather_group_info(const rv_gather* g, int group, int64_t* out5);
+rv_status rv_gather_alloc(rv_gather* g, int group, void* cuda_stream, void** out_dev_ptr);
+rv_status rv_gather_push(rv_gather* g, int group, int rank, rv_result* mine, int64_t batch, void* dst_base, void* cuda_stream);
+rv_status rv_gather_finish(rv_gather* g, int group, rv_result** out);
+void rv_gather_free(rv_gather* g);
+rv_status rv_ipc_export(void* dev_ptr, uint8_t* handle64);
+rv_status rv_ipc_open(const uint8_t* handle64, void** out_dev_ptr);
+rv_status rv_ipc_close(void* dev_ptr);
+
+/* Stand-alone device fix-ups (kept for callers that gather with their own collective): */
 /* d_dst[i] = d_src[i] + add  — rebases a shard's i32 offsets by the totals of the shards before it. */
 rv_status rv_dev_rebase_i32(int32_t* d_dst, const int32_t* d_src, int64_t n, int32_t add, void* cuda_stream);
 /* ORs nbits bits of d_src_words (LSB-first) into d_dst_words starting at bit dst_bit; the destination must be

@@ -30,6 +30,7 @@
 
 #include "../../include/ruhvro_b200.h"
 #include "arrow_c.h"
+#include "gather.hpp"
 #include "jit.hpp"
 #include "kernels.cuh"
 #include "plan.hpp"
@@ -1138,6 +1139,155 @@ WorkerPool& worker_pool(int device) {
 }
 
 }  // namespace
+
+
+// ---- multi-GPU gather (gather.hpp; pyruhvro_b200/distributed.py drives it) -----------------------------------------
+struct rv_gather {
+    rv_schema* schema = nullptr;
+    GatherPlan plan;
+    std::vector<std::shared_ptr<Arena>> arenas;  // per group; set on the group's leader by rv_gather_alloc
+    ~rv_gather() { if (schema) rv_schema_release(schema); }
+};
+
+extern "C" {
+
+int64_t rv_gather_meta_len(const rv_schema* s) { return s && s->has_plan ? gather_meta_len(s->plan) : -1; }
+
+rv_status rv_result_gather_meta(const rv_result* r, int64_t batch, int64_t* out, int64_t cap) {
+    if (!r || !out || batch < 0 || batch >= int64_t(r->chunks.size())) return fail(RV_ERR_INVALID, "bad argument");
+    if (cap < gather_meta_len(r->schema->plan)) return fail(RV_ERR_INVALID, "meta buffer too small");
+    gather_meta_of(r->schema->plan, r->chunks[size_t(batch)], out);
+    return RV_OK;
+}
+
+rv_status rv_gather_plan(const rv_schema* s, const int64_t* metas, int world, rv_gather** out) {
+    if (!s || !s->has_plan || !metas || world < 1 || !out) return fail(RV_ERR_INVALID, "bad argument");
+    try {
+        auto g = std::make_unique<rv_gather>();
+        g->schema = rv_schema_retain(const_cast<rv_schema*>(s));
+        g->plan = plan_gather(s->plan, metas, world);
+        g->arenas.resize(g->plan.groups.size());
+        *out = g.release();
+        return RV_OK;
+    } catch (const std::exception& e) {
+        return fail(RV_ERR_OVERFLOW, e.what());
+    }
+}
+
+int rv_gather_num_groups(const rv_gather* g) { return g ? int(g->plan.groups.size()) : 0; }
+int rv_gather_group_of_rank(const rv_gather* g, int rank) {
+    return g && rank >= 0 && rank < int(g->plan.group_of_rank.size()) ? g->plan.group_of_rank[size_t(rank)] : -1;
+}
+
+// out[0] = first (leader) rank, out[1] = ranks in the group, out[2] = arena bytes, out[3] = rows of the gathered batch,
+// out[4] = bytes the non-leader members push (what crosses NVLink into the leader)
+rv_status rv_gather_group_info(const rv_gather* g, int group, int64_t* out) {
+    if (!g || !out || group < 0 || group >= int(g->plan.groups.size())) return fail(RV_ERR_INVALID, "bad argument");
+    const GatherGroup& gg = g->plan.groups[size_t(group)];
+    out[0] = gg.first_rank; out[1] = gg.n_ranks; out[2] = int64_t(gg.arena_bytes); out[3] = gg.out.rows;
+    int64_t remote = 0;
+    for (size_t m = 1; m < gg.jobs.size(); ++m)
+        for (const GatherJob& j : gg.jobs[m]) remote += j.kind == GK_RAW ? j.count : (j.kind == GK_OFFSETS ? 4 * j.count : (j.count + 7) / 8);
+    out[4] = remote;
+    return RV_OK;
+}
+
+// Leader of `group`: allocates the gathered arena, zeroes it (bitmap seams are OR-merged, offsets[0] = 0) and returns
+// its device pointer.  Synchronises `cuda_stream`: the pointer may be handed to the peers right away.
+rv_status rv_gather_alloc(rv_gather* g, int group, void* cuda_stream, void** out_ptr) {
+    if (!g || !out_ptr || group < 0 || group >= int(g->plan.groups.size())) return fail(RV_ERR_INVALID, "bad argument");
+    int device = 0;
+    rv_status st = ensure_cuda(&device);
+    if (st) return st;
+    auto a = std::make_shared<Arena>();
+    a->device = device;
+    a->bytes = g->plan.groups[size_t(group)].arena_bytes;
+    a->dev = devmem().get(std::max<size_t>(a->bytes, 64), device, &a->dev_actual);
+    if (!a->dev) return fail(RV_ERR_CUDA, "device allocation of the gathered arena failed (" + std::to_string(a->bytes) + " bytes)");
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    RV_CUDA(cudaMemsetAsync(a->dev, 0, std::max<size_t>(a->bytes, 64), stream));
+    RV_CUDA(cudaStreamSynchronize(stream));
+    g->arenas[size_t(group)] = a;
+    *out_ptr = a->dev;
+    return RV_OK;
+}
+
+// Member `rank` of `group`: pushes batch `batch` of its device-resident result into the gathered arena at `dst_base`
+// (its own memory on the leader, peer memory elsewhere) with ONE kernel; synchronises `cuda_stream`.
+rv_status rv_gather_push(rv_gather* g, int group, int rank, rv_result* mine, int64_t batch, void* dst_base, void* cuda_stream) {
+    if (!g || !mine || !dst_base || group < 0 || group >= int(g->plan.groups.size())) return fail(RV_ERR_INVALID, "bad argument");
+    const GatherGroup& gg = g->plan.groups[size_t(group)];
+    const int m = rank - gg.first_rank;
+    if (m < 0 || m >= gg.n_ranks || batch < 0 || batch >= int64_t(mine->chunks.size())) return fail(RV_ERR_INVALID, "rank / batch outside the group");
+    Arena& a = *mine->arenas[size_t(batch)];
+    if (!a.dev) return fail(RV_ERR_INVALID, "the shard's batch must be device-resident");
+    const ChunkOut& c = mine->chunks[size_t(batch)];
+    const std::vector<GatherJob>& jobs = gg.jobs[size_t(m)];
+    if (jobs.empty()) return RV_OK;
+    std::vector<PushJob> pj(jobs.size());
+    int64_t bytes = 0;
+    for (size_t i = 0; i < jobs.size(); ++i) {
+        const GatherJob& j = jobs[i];
+        pj[i] = PushJob{static_cast<const uint8_t*>(a.dev) + c.slot_off[size_t(j.slot)], static_cast<uint8_t*>(dst_base) + j.dst_off, j.count, j.param, j.kind, 0};
+        bytes += j.kind == GK_RAW ? j.count : (j.kind == GK_OFFSETS ? 4 * j.count : j.count / 8);
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    DevBuf d_jobs;
+    RV_CUDA(d_jobs.alloc(pj.size() * sizeof(PushJob), stream));
+    SyncOnExit guard{stream};
+    uint8_t* h = t_scratch.get(pj.size() * sizeof(PushJob));
+    if (!h) return fail(RV_ERR_CUDA, "pinned allocation failed");
+    std::memcpy(h, pj.data(), pj.size() * sizeof(PushJob));
+    RV_CUDA(cudaMemcpyAsync(d_jobs.p, h, pj.size() * sizeof(PushJob), cudaMemcpyHostToDevice, stream));
+    const int parts = int(std::max<int64_t>(1, std::min<int64_t>(128, (bytes / int64_t(pj.size())) >> 16)));
+    launch_gather_push(static_cast<const PushJob*>(d_jobs.p), int(pj.size()), parts, stream);
+    RV_CUDA(cudaGetLastError());
+    RV_CUDA(cudaStreamSynchronize(stream));
+    guard.armed = false;
+    t_launches = 1;
+    return RV_OK;
+}
+
+// Leader of `group`, after every member pushed (the caller's barrier): the gathered batch as a device-resident result
+// (rv_result_to_host / rv_result_export / rv_result_export_device apply).
+rv_status rv_gather_finish(rv_gather* g, int group, rv_result** out) {
+    if (!g || !out || group < 0 || group >= int(g->plan.groups.size())) return fail(RV_ERR_INVALID, "bad argument");
+    if (!g->arenas[size_t(group)]) return fail(RV_ERR_INVALID, "rv_gather_alloc was not called for this group on this rank");
+    auto res = std::make_unique<rv_result>();
+    res->schema = rv_schema_retain(g->schema);
+    res->chunks.push_back(g->plan.groups[size_t(group)].out);
+    res->arenas.push_back(g->arenas[size_t(group)]);
+    res->arrow_bytes = exported_bytes(g->schema->plan, res->chunks);
+    g->arenas[size_t(group)].reset();
+    *out = res.release();
+    return RV_OK;
+}
+
+void rv_gather_free(rv_gather* g) { delete g; }
+
+// CUDA IPC plumbing for the peers' view of the leader's arena (64-byte handles).
+rv_status rv_ipc_export(void* dev_ptr, uint8_t* handle64) {
+    if (!dev_ptr || !handle64) return fail(RV_ERR_INVALID, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    RV_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    std::memcpy(handle64, &h, 64);
+    return RV_OK;
+}
+rv_status rv_ipc_open(const uint8_t* handle64, void** out) {
+    if (!handle64 || !out) return fail(RV_ERR_INVALID, "bad argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    RV_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return RV_OK;
+}
+rv_status rv_ipc_close(void* p) {
+    if (!p) return RV_OK;
+    RV_CUDA(cudaIpcCloseMemHandle(p));
+    return RV_OK;
+}
+
+}  // extern "C"
 
 extern "C" {
 

@@ -56,6 +56,64 @@ __global__ void compact_kernel(const CompactJob* jobs) {
         for (int64_t i = (nvec << 4) + threadIdx.x; i < job.bytes; i += blockDim.x) job.dst[i] = job.src[i];
 }
 
+// ---- multi-GPU gather: every rank pushes its Arrow buffers into the gathered arena on the leader GPU ----------------
+// One launch per rank, blockIdx.x = job, blockIdx.y = part of the job.  The destination is written in aligned 32-bit
+// words, consecutive lanes -> consecutive words (whole 128-byte lines per warp store over NVLink); the fix-up of each
+// buffer kind is fused into the copy:
+//   RAW      bytes at any destination alignment: each destination word is cut out of two source words (funnel shift);
+//   OFFSETS  dst[1 + i] = src[1 + i] + add   (Arrow offsets rebased by what the earlier ranks hold);
+//   BITS     the bitmap shifted to its bit position; words that other ranks share are merged with atomic OR (the arena
+//            starts zeroed), fully covered words are plain stores.
+__global__ void gather_push_kernel(const PushJob* jobs) {
+    const PushJob job = jobs[blockIdx.x];
+    const int64_t tid = int64_t(blockIdx.y) * blockDim.x + threadIdx.x, nthr = int64_t(gridDim.y) * blockDim.x;
+    if (job.kind == 1) {  // GK_OFFSETS
+        const int32_t* s = reinterpret_cast<const int32_t*>(job.src);
+        int32_t* d = reinterpret_cast<int32_t*>(job.dst);
+        const int32_t add = int32_t(job.param);
+        for (int64_t i = tid; i < job.count; i += nthr) d[1 + i] = s[1 + i] + add;
+    } else if (job.kind == 2) {  // GK_BITS
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(job.src);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(job.dst);
+        const int64_t nbits = job.count, dst_bit = job.param;
+        const int64_t w0 = dst_bit >> 5, w1 = (dst_bit + nbits + 31) >> 5;
+        const unsigned sh = unsigned(dst_bit & 31);
+        const int64_t n_src_words = (nbits + 31) >> 5;
+        for (int64_t w = w0 + tid; w < w1; w += nthr) {
+            const int64_t k = w - w0;  // source word whose low bits land at bit `sh` of this word
+            uint32_t lo = 0, hi = 0;
+            if (k < n_src_words) {
+                hi = src[k];
+                const int64_t rem = nbits - (k << 5);
+                if (rem < 32) hi &= (1u << rem) - 1u;
+            }
+            if (k >= 1 && sh) {
+                lo = src[k - 1];
+                const int64_t rem = nbits - ((k - 1) << 5);
+                if (rem < 32) lo &= (1u << rem) - 1u;
+            }
+            const uint32_t v = sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
+            const bool whole = (w << 5) >= dst_bit && ((w + 1) << 5) <= dst_bit + nbits;  // no other rank writes this word
+            if (whole) dst[w] = v;
+            else if (v) atomicOr(dst + w, v);
+        }
+    } else {  // GK_RAW
+        const uintptr_t da = reinterpret_cast<uintptr_t>(job.dst);
+        const int64_t to_word = int64_t((4u - unsigned(da & 3u)) & 3u);
+        const int64_t head = job.count < to_word ? job.count : to_word;  // bytes up to the first aligned word
+        const int64_t nwords = (job.count - head) >> 2;
+        uint32_t* dw = reinterpret_cast<uint32_t*>(job.dst + head);
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(job.src + (head & ~int64_t(3)));  // (src is 64-byte aligned, head < 4: this is src)
+        const unsigned sh = unsigned(head & 3) * 8u;
+        for (int64_t i = tid; i < nwords; i += nthr) dw[i] = sh ? __funnelshift_r(sw[i], sw[i + 1], sh) : sw[i];
+        if (blockIdx.y == 0) {
+            if (int64_t(threadIdx.x) < head) job.dst[threadIdx.x] = job.src[threadIdx.x];
+            const int64_t done = head + (nwords << 2);
+            if (done + int64_t(threadIdx.x) < job.count) job.dst[done + threadIdx.x] = job.src[done + threadIdx.x];
+        }
+    }
+}
+
 // ---- fix-ups for gathering shard-local Arrow buffers into one batch (multi-GPU) ----
 // dst[i] = src[i] + add: rebases a shard's i32 offsets by the total of the shards before it.
 __global__ void rebase_i32_kernel(int32_t* dst, const int32_t* src, long long n, int32_t add) {
@@ -114,6 +172,11 @@ void launch_fused(const DecodeParams& p, size_t smem, cudaStream_t s) {
 void launch_null_count(const NullCountJob* jobs, int n_jobs, long long* out, cudaStream_t s) {
     if (n_jobs <= 0) return;
     null_count_kernel<<<dim3(n_jobs, 16), 256, 0, s>>>(jobs, out);
+}
+
+void launch_gather_push(const PushJob* jobs, int n_jobs, int parts, cudaStream_t s) {
+    if (n_jobs <= 0) return;
+    gather_push_kernel<<<dim3(n_jobs, parts), 256, 0, s>>>(jobs);
 }
 
 void launch_compact(const CompactJob* jobs, int n_jobs, int parts, cudaStream_t s) {

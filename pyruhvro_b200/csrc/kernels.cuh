@@ -20,6 +20,16 @@ struct CompactJob {
     int64_t bytes;
 };
 
+// One push of the multi-GPU gather (gather.hpp): `dst` may be peer memory (NVLink).
+struct PushJob {
+    const uint8_t* src;   // this rank's buffer (64-byte aligned)
+    uint8_t* dst;         // where it lands in the gathered arena (RAW: any alignment; OFFSETS: element `row_base`; BITS: the bitmap's first word)
+    int64_t count;        // RAW: bytes; OFFSETS: rows; BITS: bits
+    int64_t param;        // OFFSETS: add; BITS: destination bit
+    int32_t kind;         // GatherKind
+    int32_t pad;
+};
+
 cudaError_t prepare_kernels();  // opt in to large dynamic shared memory (once per device)
 
 void launch_fused(const DecodeParams& p, size_t smem, cudaStream_t s);   // interpreter walker, one CTA per tile
@@ -27,5 +37,6 @@ void launch_rebase_i32(int32_t* dst, const int32_t* src, long long n, int32_t ad
 void launch_concat_bits(uint32_t* dst, long long dst_bit, const uint32_t* src, long long nbits, cudaStream_t s);
 void launch_null_count(const NullCountJob* jobs, int n_jobs, long long* out, cudaStream_t s);
 void launch_compact(const CompactJob* jobs, int n_jobs, int parts, cudaStream_t s);
+void launch_gather_push(const PushJob* jobs, int n_jobs, int parts, cudaStream_t s);
 
 }  // namespace rv

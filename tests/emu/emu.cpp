@@ -17,6 +17,7 @@
 
 #include "../../pyruhvro_b200/csrc/plan.hpp"
 #include "../../pyruhvro_b200/csrc/result.hpp"
+#include "../../pyruhvro_b200/csrc/gather.hpp"
 #include "../../pyruhvro_b200/csrc/schema.hpp"
 #include "../../pyruhvro_b200/csrc/interp.cuh"
 #ifdef EMU_GEN_WALKER
@@ -133,6 +134,121 @@ int count_tile(const Plan& plan, const uint8_t* data, const int64_t* off, const 
     }
     return -1;
 }
+struct Keep { std::shared_ptr<Plan> plan; std::vector<ChunkOut> chunks; uint8_t* arena; ~Keep() { std::free(arena); } };
+struct Decoded {
+    std::shared_ptr<Plan> plan;
+    std::vector<ArrowField> fields;
+    std::shared_ptr<Keep> keep;   // arena + final chunks (null counts filled)
+    int k = 0;
+};
+
+// The emulated pipeline up to (and including) null counts.  Returns 0, or the error code of the first failing record.
+int decode_core(const char* json, size_t len, const uint8_t* data, const int64_t* off, int64_t n, int64_t num_chunks, Decoded& out, int64_t* err_record) {
+    auto avro = parse_avro_schema(json, len);
+    std::string why;
+    if (!is_supported(*avro, &why)) throw std::runtime_error("unsupported: " + why);
+    out.fields = to_arrow_fields(*avro);
+    auto plan_sp = std::make_shared<Plan>(build_plan(*avro, out.fields));
+    out.plan = plan_sp;
+    const Plan& plan = *plan_sp;
+    const int S = int(plan.streams.size()), S1 = std::max(S, 1);
+    const int k = int(clamp_chunks(num_chunks, n));
+    out.k = k;
+    auto tiles = make_tiles(n, k);
+    std::vector<uint32_t> cur(size_t(S1) * kTile);
+    std::vector<std::vector<uint32_t>> tile_agg(tiles.size(), std::vector<uint32_t>(size_t(S1), 0));
+    // ---- count pass ----
+    long long fast_lanes = 0, precise_lanes = 0;
+    for (size_t ti = 0; ti < tiles.size(); ++ti) {
+        bool wp[kTile / 32];
+        uint32_t code = 0;
+        const int bad = count_tile(plan, data, off, tiles[ti], S, cur, wp, &code, &fast_lanes, &precise_lanes);
+        if (bad >= 0) { *err_record = tiles[ti].r0 + bad; return int(code); }
+        for (int s = 0; s < S; ++s) {
+            uint64_t sum = 0;
+            for (int lane = 0; lane < kTile; ++lane) sum += cur[size_t(s) * kTile + lane];
+            if (sum > 0x7FFFFFFFull) { *err_record = tiles[ti].r0; return int(E_OVERFLOW); }
+            tile_agg[ti][size_t(s)] = uint32_t(sum);
+        }
+    }
+    if (std::getenv("EMU_TRACE")) std::fprintf(stderr, "emu: %lld fast lanes, %lld precise lanes\n", fast_lanes, precise_lanes);
+    // ---- per-chunk scan ----
+    std::vector<unsigned long long> chunk_tot(size_t(k) * size_t(S1), 0ull);
+    std::vector<std::vector<uint32_t>> tile_base(tiles.size(), std::vector<uint32_t>(size_t(S1), 0));
+    for (size_t ti = 0; ti < tiles.size(); ++ti)
+        for (int s = 0; s < S; ++s) {
+            unsigned long long& tot = chunk_tot[size_t(tiles[ti].chunk) * size_t(S1) + size_t(s)];
+            tile_base[ti][size_t(s)] = uint32_t(tot);
+            tot += tile_agg[ti][size_t(s)];
+            if (tot > 0x7FFFFFFFull) { *err_record = tiles[ti].r0; return int(E_OVERFLOW); }
+        }
+    // ---- layout + arena ----
+    Layout L = compute_layout(plan, n, k, chunk_tot.data());
+    auto keep = std::make_shared<Keep>();
+    keep->plan = plan_sp;
+    keep->arena = static_cast<uint8_t*>(std::calloc(std::max<size_t>(L.total_bytes, 64), 1));
+    const int n_slots = int(plan.slots.size());
+    std::vector<void*> bufs(size_t(k) * size_t(std::max(n_slots, 1)));
+    for (int j = 0; j < k; ++j)
+        for (int sl = 0; sl < n_slots; ++sl) bufs[size_t(j) * size_t(n_slots) + size_t(sl)] = keep->arena + L.chunks[size_t(j)].slot_off[size_t(sl)];
+    // ---- emit pass ----
+    for (size_t ti = 0; ti < tiles.size(); ++ti) {
+        const Tile& t = tiles[ti];
+        void* const* cb = bufs.data() + size_t(t.chunk) * size_t(n_slots);
+        bool wp[kTile / 32];
+        uint32_t code = 0;
+        (void)count_tile(plan, data, off, t, S, cur, wp, &code, nullptr, nullptr);
+        for (int s = 0; s < S; ++s) {  // exclusive scan across lanes + tile base
+            uint32_t run = tile_base[ti][size_t(s)];
+            for (int lane = 0; lane < kTile; ++lane) { uint32_t v = cur[size_t(s) * kTile + lane]; cur[size_t(s) * kTile + lane] = run; run += v; }
+        }
+        if (t.local == 0)
+            for (const DNode& nd : plan.nodes)
+                if (nd.kind == NK_STR || nd.kind == NK_ENUM || nd.kind == NK_LIST || nd.kind == NK_MAP || nd.kind == NK_BYTES) static_cast<int32_t*>(cb[nd.slot_a])[0] = 0;
+        const std::vector<uint8_t> window = make_window(data, off, t);
+        for (int lane = 0; lane < kTile; ++lane) {
+            EmuWalker::Cur q{};
+            load_cursors(q, cur.data() + lane, S);
+            if (wp[lane / 32]) {  // a warp with a record that is not plain emits with the precise walker
+                Ctx c;
+                init_ctx(c, plan, data, off, t, lane, cur.data(), S, cb);
+                EmuWalker::walk<WM_EMIT>(c, int(plan.nodes.size()), q);
+            } else {
+                FastCtx f;
+                init_fast(f, plan, window, off, t, lane, cur.data(), cb);
+                EmuWalker::walk<WM_EMIT>(f, int(plan.nodes.size()), q);
+            }
+        }
+    }
+    // ---- null counts ----
+    for (int j = 0; j < k; ++j)
+        for (int sl : plan.validity_slots) {
+            ChunkOut& c = L.chunks[size_t(j)];
+            const int64_t bits = c.space_rows[size_t(plan.slots[size_t(sl)].space)];
+            const uint8_t* bm = keep->arena + c.slot_off[size_t(sl)];
+            int64_t ones = 0;
+            for (int64_t i = 0; i < bits; ++i) ones += (bm[i >> 3] >> (i & 7)) & 1;
+            c.null_count[size_t(sl)] = bits - ones;
+        }
+    keep->chunks = L.chunks;
+    out.keep = keep;
+    return 0;
+}
+
+// Host execution of one gather job (what gather_push_kernel does on the device), into a zero-initialised arena.
+void apply_job(const GatherJob& j, const uint8_t* src, uint8_t* dst_base) {
+    uint8_t* dst = dst_base + j.dst_off;
+    if (j.kind == GK_RAW) {
+        std::memcpy(dst, src, size_t(j.count));
+    } else if (j.kind == GK_OFFSETS) {
+        const int32_t* s = reinterpret_cast<const int32_t*>(src);
+        int32_t* d = reinterpret_cast<int32_t*>(dst);
+        for (int64_t i = 0; i < j.count; ++i) d[1 + i] = s[1 + i] + int32_t(j.param);
+    } else {
+        for (int64_t i = 0; i < j.count; ++i)
+            if ((src[i >> 3] >> (i & 7)) & 1) dst[(j.param + i) >> 3] |= uint8_t(1u << ((j.param + i) & 7));
+    }
+}
 }  // namespace
 
 extern "C" {
@@ -142,104 +258,71 @@ extern "C" {
 int emu_decode(const char* json, size_t len, const uint8_t* data, const int64_t* off, int64_t n, int64_t num_chunks,
                ArrowArray* out_batches, ArrowSchema* out_schema, int64_t* k_out, int64_t* err_record, char* msg, size_t msg_cap) {
     try {
-        auto avro = parse_avro_schema(json, len);
-        std::string why;
-        if (!is_supported(*avro, &why)) throw std::runtime_error("unsupported: " + why);
-        auto fields = to_arrow_fields(*avro);
-        auto plan_sp = std::make_shared<Plan>(build_plan(*avro, fields));
-        const Plan& plan = *plan_sp;
-        const int S = int(plan.streams.size()), S1 = std::max(S, 1);
-        const int k = int(clamp_chunks(num_chunks, n));
-        *k_out = k;
-        auto tiles = make_tiles(n, k);
-        std::vector<uint32_t> cur(size_t(S1) * kTile);
-        std::vector<std::vector<uint32_t>> tile_agg(tiles.size(), std::vector<uint32_t>(size_t(S1), 0));
-        // ---- count pass ----
-        std::vector<char> precise_warp(tiles.size() * size_t(kTile / 32), 0);
-        long long fast_lanes = 0, precise_lanes = 0;
-        for (size_t ti = 0; ti < tiles.size(); ++ti) {
-            bool wp[kTile / 32];
-            uint32_t code = 0;
-            const int bad = count_tile(plan, data, off, tiles[ti], S, cur, wp, &code, &fast_lanes, &precise_lanes);
-            if (bad >= 0) { *err_record = tiles[ti].r0 + bad; return int(code); }
-            for (int w = 0; w < kTile / 32; ++w) precise_warp[ti * size_t(kTile / 32) + size_t(w)] = wp[w];
-            for (int s = 0; s < S; ++s) {
-                uint64_t sum = 0;
-                for (int lane = 0; lane < kTile; ++lane) sum += cur[size_t(s) * kTile + lane];
-                if (sum > 0x7FFFFFFFull) { *err_record = tiles[ti].r0; return int(E_OVERFLOW); }
-                tile_agg[ti][size_t(s)] = uint32_t(sum);
-            }
-        }
-        if (std::getenv("EMU_TRACE")) std::fprintf(stderr, "emu: %lld fast lanes, %lld precise lanes\n", fast_lanes, precise_lanes);
-        // ---- per-chunk scan ----
-        std::vector<unsigned long long> chunk_tot(size_t(k) * size_t(S1), 0ull);
-        std::vector<std::vector<uint32_t>> tile_base(tiles.size(), std::vector<uint32_t>(size_t(S1), 0));
-        for (size_t ti = 0; ti < tiles.size(); ++ti)
-            for (int s = 0; s < S; ++s) {
-                unsigned long long& tot = chunk_tot[size_t(tiles[ti].chunk) * size_t(S1) + size_t(s)];
-                tile_base[ti][size_t(s)] = uint32_t(tot);
-                tot += tile_agg[ti][size_t(s)];
-                if (tot > 0x7FFFFFFFull) { *err_record = tiles[ti].r0; return int(E_OVERFLOW); }
-            }
-        // ---- layout + arena ----
-        Layout L = compute_layout(plan, n, k, chunk_tot.data());
-        struct Keep { std::shared_ptr<Plan> plan; std::vector<ChunkOut> chunks; uint8_t* arena; ~Keep() { std::free(arena); } };
-        auto keep = std::make_shared<Keep>();
-        keep->plan = plan_sp;
-        keep->arena = static_cast<uint8_t*>(std::calloc(std::max<size_t>(L.total_bytes, 64), 1));
-        // poison everything that the device does not zero, to catch missing writes
-        std::memset(keep->arena + L.zero_bytes, 0, L.total_bytes - L.zero_bytes);
-        const int n_slots = int(plan.slots.size());
-        std::vector<void*> bufs(size_t(k) * size_t(std::max(n_slots, 1)));
-        for (int j = 0; j < k; ++j)
-            for (int sl = 0; sl < n_slots; ++sl) bufs[size_t(j) * size_t(n_slots) + size_t(sl)] = keep->arena + L.chunks[size_t(j)].slot_off[size_t(sl)];
-        // ---- emit pass ----
-        for (size_t ti = 0; ti < tiles.size(); ++ti) {
-            const Tile& t = tiles[ti];
-            void* const* cb = bufs.data() + size_t(t.chunk) * size_t(n_slots);
-            bool wp[kTile / 32];
-            uint32_t code = 0;
-            (void)count_tile(plan, data, off, t, S, cur, wp, &code, nullptr, nullptr);
-            for (int s = 0; s < S; ++s) {  // exclusive scan across lanes + tile base
-                uint32_t run = tile_base[ti][size_t(s)];
-                for (int lane = 0; lane < kTile; ++lane) { uint32_t v = cur[size_t(s) * kTile + lane]; cur[size_t(s) * kTile + lane] = run; run += v; }
-            }
-            if (t.local == 0)
-                for (const DNode& nd : plan.nodes)
-                    if (nd.kind == NK_STR || nd.kind == NK_ENUM || nd.kind == NK_LIST || nd.kind == NK_MAP || nd.kind == NK_BYTES) static_cast<int32_t*>(cb[nd.slot_a])[0] = 0;
-            const std::vector<uint8_t> window = make_window(data, off, t);
-            for (int lane = 0; lane < kTile; ++lane) {
-                EmuWalker::Cur q{};
-                load_cursors(q, cur.data() + lane, S);
-                if (wp[lane / 32]) {  // a warp with a record that is not plain emits with the precise walker
-                    Ctx c;
-                    init_ctx(c, plan, data, off, t, lane, cur.data(), S, cb);
-                    EmuWalker::walk<WM_EMIT>(c, int(plan.nodes.size()), q);
-                } else {
-                    FastCtx f;
-                    init_fast(f, plan, window, off, t, lane, cur.data(), cb);
-                    EmuWalker::walk<WM_EMIT>(f, int(plan.nodes.size()), q);
-                }
-            }
-        }
-        // ---- null counts ----
-        for (int j = 0; j < k; ++j)
-            for (int sl : plan.validity_slots) {
-                ChunkOut& c = L.chunks[size_t(j)];
-                const int64_t bits = c.space_rows[size_t(plan.slots[size_t(sl)].space)];
-                const uint8_t* bm = keep->arena + c.slot_off[size_t(sl)];
-                int64_t ones = 0;
-                for (int64_t i = 0; i < bits; ++i) ones += (bm[i >> 3] >> (i & 7)) & 1;
-                c.null_count[size_t(sl)] = bits - ones;
-            }
-        keep->chunks = L.chunks;
-        for (int j = 0; j < k; ++j) export_batch(plan, keep->chunks[size_t(j)], keep->arena, keep, &out_batches[j]);
-        if (out_schema) export_arrow_schema(fields, out_schema);
+        Decoded d;
+        const int rc = decode_core(json, len, data, off, n, num_chunks, d, err_record);
+        *k_out = d.k;
+        if (rc) return rc;
+        for (int j = 0; j < d.k; ++j) export_batch(*d.plan, d.keep->chunks[size_t(j)], d.keep->arena, d.keep, &out_batches[j]);
+        if (out_schema) export_arrow_schema(d.fields, out_schema);
         return 0;
     } catch (const std::exception& e) {
         std::snprintf(msg, msg_cap, "%s", e.what());
         return -1;
     }
+}
+
+// ---- multi-rank gather on the host: the product's plan (gather.cpp), the kernel's job semantics restated ------------
+// A decoded shard (one batch) kept for the gather steps.
+void* emu_shard_decode(const char* json, size_t len, const uint8_t* data, const int64_t* off, int64_t n, char* msg, size_t msg_cap) {
+    try {
+        auto d = std::make_unique<Decoded>();
+        int64_t rec = -1;
+        if (decode_core(json, len, data, off, n, 1, *d, &rec) != 0) throw std::runtime_error("decode error in shard");
+        return d.release();
+    } catch (const std::exception& e) {
+        std::snprintf(msg, msg_cap, "%s", e.what());
+        return nullptr;
+    }
+}
+void emu_shard_free(void* h) { delete static_cast<Decoded*>(h); }
+int64_t emu_meta_len(void* h) { return gather_meta_len(*static_cast<Decoded*>(h)->plan); }
+void emu_shard_meta(void* h, int64_t* out) {
+    auto* d = static_cast<Decoded*>(h);
+    gather_meta_of(*d->plan, d->keep->chunks[0], out);
+}
+// out[0] = groups; then per group: first rank, ranks, arena bytes, rows
+int emu_gather_groups(void* h, const int64_t* metas, int world, int64_t* out, int cap) {
+    auto* d = static_cast<Decoded*>(h);
+    GatherPlan gp = plan_gather(*d->plan, metas, world);
+    out[0] = int64_t(gp.groups.size());
+    for (size_t i = 0; i < gp.groups.size() && int(1 + 4 * (i + 1)) <= cap; ++i) {
+        out[1 + 4 * i] = gp.groups[i].first_rank; out[2 + 4 * i] = gp.groups[i].n_ranks;
+        out[3 + 4 * i] = int64_t(gp.groups[i].arena_bytes); out[4 + 4 * i] = gp.groups[i].out.rows;
+    }
+    return 0;
+}
+// Applies `rank`'s jobs into `arena` (the arena of the rank's group, zero-initialised by the caller).
+int emu_gather_apply(void* h, const int64_t* metas, int world, int rank, uint8_t* arena) {
+    auto* d = static_cast<Decoded*>(h);
+    GatherPlan gp = plan_gather(*d->plan, metas, world);
+    const GatherGroup& g = gp.groups[size_t(gp.group_of_rank[size_t(rank)])];
+    const ChunkOut& mine = d->keep->chunks[0];
+    for (const GatherJob& j : g.jobs[size_t(rank - g.first_rank)]) apply_job(j, d->keep->arena + mine.slot_off[size_t(j.slot)], arena);
+    return 0;
+}
+// Exports the gathered batch of `group` from a finished arena (copied).
+int emu_gather_export(void* h, const int64_t* metas, int world, int group, const uint8_t* arena, ArrowArray* out, ArrowSchema* out_schema) {
+    auto* d = static_cast<Decoded*>(h);
+    GatherPlan gp = plan_gather(*d->plan, metas, world);
+    const GatherGroup& g = gp.groups[size_t(group)];
+    auto keep = std::make_shared<Keep>();
+    keep->plan = d->plan;
+    keep->arena = static_cast<uint8_t*>(std::malloc(std::max<size_t>(g.arena_bytes, 64)));
+    std::memcpy(keep->arena, arena, g.arena_bytes);
+    keep->chunks = {g.out};
+    export_batch(*d->plan, keep->chunks[0], keep->arena, keep, out);
+    if (out_schema) export_arrow_schema(d->fields, out_schema);
+    return 0;
 }
 
 }  // extern "C"

@@ -1,10 +1,13 @@
-"""world_size-2 gloo tests of the multi-GPU gather's host logic (shard partition, size exchange,
-offset rebasing order, bitmap seams, lazily-absent validity).  The shard-local batches come from the
-oracle and the two device fix-up kernels are replaced by numpy stand-ins from tests/dist_helpers.py;
-the real NCCL + CUDA path is exercised by tests/dist_gpu_check.py on a multi-GPU box."""
+"""world_size-2 gloo tests of the multi-GPU gather's host side: shard partition, the ONE exchange of sizes
+(pyruhvro_b200.distributed._all_gather_i64 over the process group), the product's gather plan (csrc/gather.cpp: groups,
+prefix offsets, rebase amounts, bit positions) and the semantics of every push job.  The shards are decoded by the host
+emulation (tests/emu) and each rank applies its jobs to a zeroed copy of the gathered arena; a bitwise-OR reduce to the
+leader stands in for the NVLink stores (the ranks' pushes touch disjoint bytes except for OR-merged bitmap seams).
+The NCCL + CUDA IPC + push-kernel path itself is exercised by tests/test_gpu_gather.py."""
 import os
 import random
 
+import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
@@ -12,7 +15,7 @@ import torch.multiprocessing as mp
 
 from oracle import pyoracle as po
 from pyruhvro_b200 import distributed as D
-from tests.parity import expected_schema, gen_case
+from tests.parity import gen_case
 
 
 def test_shard_bounds_cover_and_align():
@@ -24,29 +27,48 @@ def test_shard_bounds_cover_and_align():
         assert all(x[0] % 256 == 0 for x in b if x[0] < n or n == 0)
 
 
+def test_plan_splits_at_the_i32_ceiling():
+    """100 M rows of the Kafka schema hold ~3.3 GB of e-mail bytes: more than one Arrow batch can address.  The plan
+    groups consecutive ranks into as few batches as fit."""
+    import workloads
+    from tests import emu
+    sj, data, off = workloads.generate("kafka", 2000, seed=1)
+    sh = emu.Shard(sj, data, off, 2000)
+    m = sh.meta()
+    per_rank = m * 6250                                   # what a 12.5 M-row shard of the same data would report
+    metas = np.stack([per_rank] * 8)
+    groups = sh.groups(metas)
+    assert len(groups) >= 2 and sum(g[1] for g in groups) == 8 and [g[0] for g in groups] == sorted(g[0] for g in groups)
+    assert all(g[3] == 12_500_000 * g[1] for g in groups)
+    assert len(sh.groups(np.stack([m] * 8))) == 1          # small shards: one batch
+
+
 def _worker(rank, world, port, seeds, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from tests.dist_helpers import NumpyOps, flat_from_canon
+    from tests import emu
     co = po.COracle()
     try:
         for seed in seeds:
             sj, recs, data, off = gen_case(seed, n=random.Random(seed).choice([600, 1000, 1301]))
             n = len(recs)
-            schema = po.to_arrow_schema(po.parse_schema(sj))
             r0, r1 = D.shard_bounds(n, world, rank)
-            local_cols = co.decode(sj, recs[r0:r1])
-            local = flat_from_canon(local_cols, schema)
-            batch = D.gather_batch(local, schema, ops=NumpyOps(), device="cpu")
-            want = co.decode(sj, recs)
-            batch.validate(full=True)
-            got = po.canon_from_batch(batch)
-            # a shard-local lazily-absent bitmap may become present after the gather; compare logically there
-            diff = po.canon_diff(got, want)
-            if diff is not None and "validity presence" not in diff:
-                raise AssertionError(f"seed {seed} rank {rank}: {diff}")
-            assert batch.equals(po.canon_to_batch(want, schema)), f"seed {seed}: logical mismatch"
+            d, o = po.pack_records(recs[r0:r1])
+            shard = emu.Shard(sj, d, o, r1 - r0)
+            metas = D._all_gather_i64(shard.meta(), None, torch.device("cpu"))       # the product's size exchange
+            groups = shard.groups(metas)
+            assert len(groups) == 1 and groups[0][0] == 0 and groups[0][1] == world and groups[0][3] == n
+            arena = np.zeros(max(groups[0][2], 64), dtype=np.uint8)
+            shard.apply(metas, rank, arena)
+            t = torch.from_numpy(arena)
+            dist.reduce(t, dst=0, op=dist.ReduceOp.BOR)
+            if rank == 0:
+                batch = shard.export(metas, 0, arena)
+                batch.validate(full=True)
+                diff = po.canon_diff(po.canon_from_batch(batch), co.decode(sj, recs))
+                if diff is not None:
+                    raise AssertionError(f"seed {seed}: {diff}")
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, f"FAIL {type(e).__name__}: {e}"))
