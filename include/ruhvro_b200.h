@@ -49,7 +49,8 @@ typedef enum rv_status {
     RV_ERR_OVERFLOW = 8,     /* a column of one batch exceeds Arrow's i32 offsets (arrow-rs panics here) */
     RV_ERR_INVALID = 9,      /* bad argument */
     RV_ERR_CUDA = 10,        /* CUDA runtime failure (includes "no device") */
-    RV_ERR_VALUE = 11        /* wider subset: uuid text that is not a UUID, decimal wider than 128 bits */
+    RV_ERR_VALUE = 11,       /* wider subset: uuid text that is not a UUID, decimal wider than 128 bits */
+    RV_ERR_FRAME = 12        /* framed input: message shorter than its header, wrong magic byte, unexpected schema id */
 } rv_status;
 
 /* ---- schema --------------------------------------------------------------------------- */
@@ -91,6 +92,28 @@ rv_status rv_decode_host(const rv_schema* s, const uint8_t* data, const int64_t*
  * the same schema handle needed, so they may carry a few per cent of slack between them. */
 rv_status rv_decode_device(const rv_schema* s, const uint8_t* d_data, const int64_t* d_offsets, int64_t n,
                            int64_t num_chunks, void* cuda_stream, rv_result** out);
+
+/* Framed inputs — the step before the path in Kafka pipelines.  The reference takes bare datums
+ * only (README.md:93-94: callers strip the Confluent header themselves, one Python slice per message); here the strip is
+ * offset arithmetic inside the decode kernel: record i is still data[offsets[i] .. offsets[i+1]), but its datum starts
+ * `header_bytes` later.  check_magic != 0 validates the Confluent wire format's header (byte 0 = 0x00; with
+ * schema_id >= 0 also the big-endian u32 schema id in bytes 1..4): a mismatch is RV_ERR_FRAME with the record index. */
+typedef struct rv_framing {
+    int32_t header_bytes;  /* bytes to skip at the start of every message (Confluent: 5) */
+    int32_t check_magic;   /* 0: skip only; 1: check the Confluent magic byte (and the id when schema_id >= 0) */
+    int64_t schema_id;     /* -1: any */
+} rv_framing;
+rv_status rv_decode_host_framed(const rv_schema* s, const uint8_t* data, const int64_t* offsets, int64_t n,
+                                int64_t num_chunks, const rv_framing* framing, rv_result** out);
+rv_status rv_decode_device_framed(const rv_schema* s, const uint8_t* d_data, const int64_t* d_offsets, int64_t n,
+                                  int64_t num_chunks, const rv_framing* framing, void* cuda_stream, rv_result** out);
+
+/* An Avro Object Container File (magic, header with avro.schema / avro.codec, blocks of datums between sync markers;
+ * uncompressed blocks only) -> `num_chunks` batches in pinned host memory.  The schema comes from the file: a new handle is
+ * returned in *schema_out (release it with rv_schema_release).  Datums inside a block carry no lengths: the host walks
+ * the block headers, a kernel with one lane per block walks the records to find their offsets, then the decode kernel
+ * runs as on any packed input.  A malformed container is RV_ERR_FRAME. */
+rv_status rv_decode_ocf_host(const uint8_t* file, int64_t len, int64_t num_chunks, rv_schema** schema_out, rv_result** out);
 
 /* Copies a device-resident result's buffers to pinned host memory (no-op if already there). */
 rv_status rv_result_to_host(rv_result* r);

@@ -31,6 +31,7 @@ from . import _build
 __all__ = [
     "deserialize_array", "deserialize_array_threaded", "deserialize_array_threaded_spawn",
     "serialize_record_batch", "serialize_record_batch_spawn", "lib", "Schema", "decode_packed", "deserialize_arrow_array",
+    "deserialize_confluent", "deserialize_ocf",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -65,6 +66,9 @@ def _load():
     L.rv_schema_export_arrow.argtypes = [vp, vp]
     L.rv_decode_host.argtypes = [vp, vp, vp, i64, i64, ctypes.POINTER(vp)]
     L.rv_decode_device.argtypes = [vp, vp, vp, i64, i64, vp, ctypes.POINTER(vp)]
+    L.rv_decode_host_framed.argtypes = [vp, vp, vp, i64, i64, vp, ctypes.POINTER(vp)]
+    L.rv_decode_device_framed.argtypes = [vp, vp, vp, i64, i64, vp, vp, ctypes.POINTER(vp)]
+    L.rv_decode_ocf_host.argtypes = [vp, i64, i64, ctypes.POINTER(vp), ctypes.POINTER(vp)]
     L.rv_result_to_host.argtypes = [vp]
     L.rv_result_num_batches.restype = i64
     L.rv_result_num_batches.argtypes = [vp]
@@ -204,12 +208,43 @@ def _ext():
     return importlib.import_module(__name__ + "._native")  # built by _build.build_ext(); ImportError is the loud failure
 
 
-def _decode_list(records, schema: str, num_chunks: int) -> List[pa.RecordBatch]:
+class Framing(ctypes.Structure):
+    """rv_framing (include/ruhvro_b200.h): per-message header to skip, optionally validated as a Confluent header."""
+    _fields_ = [("header_bytes", ctypes.c_int32), ("check_magic", ctypes.c_int32), ("schema_id", ctypes.c_int64)]
+
+
+def _decode_list(records, schema: str, num_chunks: int, framing=None) -> List[pa.RecordBatch]:
     if not isinstance(records, list):
         raise TypeError("argument 'list': expected a list of bytes")
     s = _get_or_parse_schema(schema)
-    handle = _ext().decode_list(s.handle, records, int(num_chunks))
+    if framing is None:
+        handle = _ext().decode_list(s.handle, records, int(num_chunks))
+    else:
+        handle = _ext().decode_list(s.handle, records, int(num_chunks), *framing)
     return _export_batches(handle, s)
+
+
+def deserialize_ocf(data, num_chunks=1) -> List[pa.RecordBatch]:
+    """The bytes of an Avro Object Container File (uncompressed blocks) -> `num_chunks` RecordBatches; the schema is the
+    file's own.  Record boundaries are found on the GPU (one lane per block), see include/ruhvro_b200.h."""
+    import numpy as np
+    if num_chunks < 0:
+        raise OverflowError("can't convert negative int to unsigned")
+    buf = np.frombuffer(data, dtype=np.uint8)
+    sh, h = ctypes.c_void_p(), ctypes.c_void_p()
+    _check(lib.rv_decode_ocf_host(buf.ctypes.data if buf.size else None, buf.size, int(num_chunks), ctypes.byref(sh), ctypes.byref(h)))
+    s = Schema.__new__(Schema)
+    s.handle, s._arrow = sh.value, None
+    return _export_batches(h.value, s)
+
+
+def deserialize_confluent(list, schema, num_chunks=1, schema_id=None):  # noqa: A002
+    """list[bytes] of Confluent-framed Kafka messages (magic 0x00 + big-endian u32 schema id + Avro datum) ->
+    `num_chunks` RecordBatches.  The 5-byte header is validated (the id too when `schema_id` is given) and skipped inside
+    the decode kernel — no per-message slicing in Python (the reference expects callers to strip it, README.md:93-94)."""
+    if num_chunks < 0:
+        raise OverflowError("can't convert negative int to unsigned")
+    return _decode_list(list, schema, num_chunks, framing=(5, 1, -1 if schema_id is None else int(schema_id)))
 
 
 def deserialize_array(list, schema):  # noqa: A002 - the reference names the parameter `list`
@@ -231,15 +266,16 @@ def deserialize_array_threaded_spawn(list, schema, num_chunks):  # noqa: A002
     return deserialize_array_threaded(list, schema, num_chunks)
 
 
-def decode_packed(data, offsets, n: int, schema: str, num_chunks: int = 1) -> List[pa.RecordBatch]:
-    """Packed host buffers (numpy uint8 data + int64 offsets[n+1]) -> batches, through rv_decode_host.
-    This is the C-ABI call a Rust/FFI caller makes; no Python list walk involved."""
+def decode_packed(data, offsets, n: int, schema: str, num_chunks: int = 1, framing: "Framing | None" = None) -> List[pa.RecordBatch]:
+    """Packed host buffers (numpy uint8 data + int64 offsets[n+1]) -> batches, through rv_decode_host (or
+    rv_decode_host_framed when `framing` is given).  This is the C-ABI call a Rust/FFI caller makes; no Python list walk."""
     import numpy as np
     s = _get_or_parse_schema(schema)
     data = np.ascontiguousarray(data, dtype=np.uint8)
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     h = ctypes.c_void_p()
-    _check(lib.rv_decode_host(s.handle, data.ctypes.data if data.size else None, offsets.ctypes.data, n, num_chunks, ctypes.byref(h)))
+    _check(lib.rv_decode_host_framed(s.handle, data.ctypes.data if data.size else None, offsets.ctypes.data, n, num_chunks,
+                                     ctypes.byref(framing) if framing is not None else None, ctypes.byref(h)))
     return _export_batches(h.value, s)
 
 

@@ -247,6 +247,16 @@ __device__ __forceinline__ int64_t init_ctx(C& c, const DecodeParams& p, const T
             c.base = p.data + o0;
             c.end = uint32_t(o1 - o0);
         }
+        if (p.frame_skip && !c.err) {  // framed input: the datum starts behind the message's header
+            if (c.end - c.pos < p.frame_skip) c.err = E_FRAME;
+            else {
+                if (p.frame_check) {
+                    const uint32_t id = (ld_u8(c, c.pos + 1) << 24) | (ld_u8(c, c.pos + 2) << 16) | (ld_u8(c, c.pos + 3) << 8) | ld_u8(c, c.pos + 4);
+                    if (ld_u8(c, c.pos) != 0u || (p.frame_check == 2 && id != p.frame_id)) c.err = E_FRAME;
+                }
+                c.pos += p.frame_skip;
+            }
+        }
     }
     return r;
 }

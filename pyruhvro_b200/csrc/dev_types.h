@@ -86,6 +86,7 @@ enum ErrCode : uint32_t {
     E_ENUM = 6,      // "enum index out of range" (:575)
     E_SCHEMA = 7,
     E_OVERFLOW = 8,  // i32 Arrow offset overflow (arrow-rs panics; reported as an error)
+    E_FRAME = 12,    // framed input: message shorter than its header / wrong magic byte / wrong schema id
     E_VALUE = 11     // wider subset: a value its logical type cannot hold (uuid text that is not a UUID, decimal wider than 128 bits)
 };
 
@@ -137,6 +138,11 @@ struct DecodeParams {
     uint32_t smem_data_cap;   // bytes of shared memory for staging a tile's input bytes
     uint32_t smem_stage_cap;  // bytes of shared memory for staging a tile's Utf8 output bytes
     int32_t count_only;       // 1: validate + totals only (no buffers yet)
+    // framed input: every message starts with `frame_skip` header bytes that are not part of the datum (Confluent wire
+    // format: magic 0x00 + big-endian u32 schema id).  frame_check: 0 skip only, 1 check the magic byte, 2 also the id
+    uint32_t frame_skip;
+    int32_t frame_check;
+    uint32_t frame_id;
 };
 
 // Readers may run a few tokens past a record's end before the deferred end-of-buffer check notices (dev_core.cuh):

@@ -31,6 +31,7 @@
 #include "../../include/ruhvro_b200.h"
 #include "arrow_c.h"
 #include "gather.hpp"
+#include "ocf.hpp"
 #include "jit.hpp"
 #include "kernels.cuh"
 #include "plan.hpp"
@@ -507,6 +508,7 @@ const char* err_text(uint32_t code) {
         case E_ENUM: return "enum index out of range";
         case E_OVERFLOW: return "Arrow i32 offset overflow (or malformed input offsets)";
         case E_VALUE: return "value does not fit its logical type (uuid text / decimal wider than 128 bits)";
+        case E_FRAME: return "framed message: shorter than its header, wrong magic byte or unexpected schema id";
         default: return "decode error";
     }
 }
@@ -560,6 +562,7 @@ struct SyncOnExit {
 struct InputHints {
     int64_t total_bytes = -1;
     int64_t max_span = -1;
+    rv_framing framing = {0, 0, -1};   // framed input (rv_decode_*_framed)
 };
 
 // ---- the decode call ------------------------------------------------------------------------
@@ -638,6 +641,9 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
     p.sym_off = dp.sym_off; p.sym_bytes = dp.sym_bytes; p.stream_slot = dp.stream_slot;
     p.n_utf8 = 0;
     for (int i = 0; i < S; ++i) p.n_utf8 += plan.streams[size_t(i)].is_rows ? 0 : 1;
+    p.frame_skip = uint32_t(std::max(hints.framing.header_bytes, 0));
+    p.frame_check = hints.framing.check_magic ? (hints.framing.schema_id >= 0 ? 2 : 1) : 0;
+    p.frame_id = uint32_t(hints.framing.schema_id >= 0 ? hints.framing.schema_id : 0);
 
     // ---- shared-memory windows: [fixed tables][input window (+pad)][Utf8 staging / scan area] ----------
     const size_t limit = 227 * 1024;
@@ -930,11 +936,21 @@ rv_status rv_schema_export_arrow(const rv_schema* s, struct ArrowSchema* out) {
     }
 }
 
-rv_status rv_decode_device(const rv_schema* s, const uint8_t* d_data, const int64_t* d_offsets, int64_t n,
-                           int64_t num_chunks, void* cuda_stream, rv_result** out) {
+static rv_status framing_ok(const rv_framing* f) {
+    if (!f) return RV_OK;
+    if (f->header_bytes < 0 || f->header_bytes > 4096) return fail(RV_ERR_INVALID, "framing: header_bytes out of range");
+    if (f->check_magic && f->header_bytes < 5) return fail(RV_ERR_INVALID, "framing: the Confluent header check needs header_bytes >= 5");
+    if (f->schema_id > int64_t(0xFFFFFFFFu)) return fail(RV_ERR_INVALID, "framing: schema_id is a u32");
+    return RV_OK;
+}
+
+rv_status rv_decode_device_framed(const rv_schema* s, const uint8_t* d_data, const int64_t* d_offsets, int64_t n,
+                                  int64_t num_chunks, const rv_framing* framing, void* cuda_stream, rv_result** out) {
     if (!out) return fail(RV_ERR_INVALID, "null argument");
     *out = nullptr;
     rv_status st = check_decodable(s);
+    if (st) return st;
+    st = framing_ok(framing);
     if (st) return st;
     if (n < 0 || (n > 0 && (!d_data || !d_offsets))) return fail(RV_ERR_INVALID, "bad input pointers");
     if (reinterpret_cast<uintptr_t>(d_data) & 15u) return fail(RV_ERR_INVALID, "d_data must be 16-byte aligned");
@@ -942,14 +958,21 @@ rv_status rv_decode_device(const rv_schema* s, const uint8_t* d_data, const int6
     st = ensure_cuda(&device);
     if (st) return st;
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    InputHints hints;
+    if (framing) hints.framing = *framing;
     try {
-        st = decode_on_device(const_cast<rv_schema*>(s), d_data, d_offsets, n, num_chunks, InputHints{}, stream, device, out);
+        st = decode_on_device(const_cast<rv_schema*>(s), d_data, d_offsets, n, num_chunks, hints, stream, device, out);
     } catch (const std::exception& e) {
         st = fail(RV_ERR_INVALID, e.what());
     }
     // error paths hand cached device blocks back: nothing may still be running on them
     if (st) { const std::string keep = t_error; cudaStreamSynchronize(stream); (void)cudaGetLastError(); t_error = keep; }
     return st;
+}
+
+rv_status rv_decode_device(const rv_schema* s, const uint8_t* d_data, const int64_t* d_offsets, int64_t n,
+                           int64_t num_chunks, void* cuda_stream, rv_result** out) {
+    return rv_decode_device_framed(s, d_data, d_offsets, n, num_chunks, nullptr, cuda_stream, out);
 }
 
 }  // extern "C"
@@ -1028,10 +1051,11 @@ rv_status arena_to_host(rv_result& r, Arena& a, cudaStream_t stream, float* ms) 
 
 // H2D of rows [r0, r1) of the caller's packed input, decode into `num_chunks` batches, D2H.
 rv_status decode_host_range(rv_schema* s, const uint8_t* data, const int64_t* offsets, int64_t r0, int64_t r1, int64_t num_chunks,
-                            cudaStream_t stream, int device, rv_result** out, float* h2d_ms, float* d2h_ms) {
+                            cudaStream_t stream, int device, rv_result** out, float* h2d_ms, float* d2h_ms, const rv_framing& framing) {
     const int64_t n = r1 - r0;
     DevBuf d_data, d_off;
     InputHints hints;
+    hints.framing = framing;
     const uint8_t* base = nullptr;
     rv_status st = RV_OK;
     if (n > 0) {
@@ -1289,6 +1313,79 @@ rv_status rv_ipc_close(void* p) {
 
 }  // extern "C"
 
+
+// ---- Avro object container files (ocf.hpp) ---------------------------------------------------------------------------
+extern "C" rv_status rv_decode_ocf_host(const uint8_t* file, int64_t len, int64_t num_chunks, rv_schema** schema_out, rv_result** out) {
+    if (!file || len < 0 || !schema_out || !out) return fail(RV_ERR_INVALID, "null argument");
+    *schema_out = nullptr;
+    *out = nullptr;
+    OcfIndex ix;
+    try {
+        ix = ocf_index(file, len);
+    } catch (const std::exception& e) {
+        return fail(RV_ERR_FRAME, e.what());
+    }
+    rv_schema* s = nullptr;
+    rv_status st = rv_schema_parse(ix.schema_json.data(), ix.schema_json.size(), &s);
+    if (st) return st;
+    struct Release { rv_schema* s; bool armed = true; ~Release() { if (armed) rv_schema_release(s); } } rel{s};
+    st = check_decodable(s);
+    if (st) return st;
+    int device = 0;
+    st = ensure_cuda(&device);
+    if (st) return st;
+    cudaStream_t stream = nullptr;
+    const int64_t n = ix.n_records;
+    DevBuf d_file, d_blocks, d_off, d_err;
+    RV_CUDA(d_file.alloc(size_t(len) + 64, stream));
+    RV_CUDA(d_off.alloc(size_t(n + 1) * 8, stream));
+    RV_CUDA(d_err.alloc(16, stream));
+    SyncOnExit guard{stream};
+    RV_CUDA(cudaMemcpyAsync(d_file.p, file, size_t(len), cudaMemcpyHostToDevice, stream));
+    if (n > 0) {
+        DevicePlan dp;
+        st = device_plan(s, device, &dp);
+        if (st) return st;
+        std::vector<OcfBlockDev> blocks(ix.blocks.size());
+        for (size_t i = 0; i < blocks.size(); ++i) blocks[i] = OcfBlockDev{ix.blocks[i].data_off, ix.blocks[i].size, ix.blocks[i].count, ix.blocks[i].rec_base};
+        RV_CUDA(d_blocks.alloc(blocks.size() * sizeof(OcfBlockDev), stream));
+        RV_CUDA(cudaMemcpyAsync(d_blocks.p, blocks.data(), blocks.size() * sizeof(OcfBlockDev), cudaMemcpyHostToDevice, stream));
+        RV_CUDA(cudaMemsetAsync(d_err.p, 0xFF, 8, stream));
+        OcfParams q{};
+        q.data = static_cast<const uint8_t*>(d_file.p);
+        q.blocks = static_cast<const OcfBlockDev*>(d_blocks.p);
+        q.n_blocks = int32_t(blocks.size());
+        q.nodes = dp.nodes; q.n_nodes = int32_t(s->plan.nodes.size());
+        q.sym_off = dp.sym_off; q.sym_bytes = dp.sym_bytes;
+        q.offsets = static_cast<int64_t*>(d_off.p);
+        q.n_records = n;
+        q.end_off = ix.end_off;
+        q.err = static_cast<unsigned long long*>(d_err.p);
+        launch_ocf_offsets(q, stream);
+        RV_CUDA(cudaGetLastError());
+        unsigned long long err_word = ~0ull;
+        RV_CUDA(cudaMemcpyAsync(&err_word, d_err.p, 8, cudaMemcpyDeviceToHost, stream));
+        RV_CUDA(cudaStreamSynchronize(stream));   // (the block table on the host stack is done with as well)
+        if (err_word != ~0ull) {
+            const uint32_t code = uint32_t(err_word & 0xFF);
+            return fail(rv_status(code), std::string(err_text(code)) + " (record " + std::to_string(int64_t(err_word >> 8)) + ")");
+        }
+    }
+    try {
+        st = decode_on_device(s, static_cast<const uint8_t*>(d_file.p), static_cast<const int64_t*>(d_off.p), n, num_chunks, InputHints{}, stream, device, out);
+    } catch (const std::exception& e) {
+        st = fail(RV_ERR_INVALID, e.what());
+    }
+    if (st) return st;
+    float ms = 0;
+    st = arena_to_host(**out, *(*out)->arenas[0], stream, &ms);
+    if (st) { rv_result_free(*out); *out = nullptr; return st; }
+    guard.armed = false;
+    rel.armed = false;
+    *schema_out = s;
+    return RV_OK;
+}
+
 extern "C" {
 
 rv_status rv_result_to_host(rv_result* r) {
@@ -1304,11 +1401,19 @@ rv_status rv_result_to_host(rv_result* r) {
 
 rv_status rv_decode_host(const rv_schema* s_, const uint8_t* data, const int64_t* offsets, int64_t n,
                          int64_t num_chunks, rv_result** out) {
+    return rv_decode_host_framed(s_, data, offsets, n, num_chunks, nullptr, out);
+}
+
+rv_status rv_decode_host_framed(const rv_schema* s_, const uint8_t* data, const int64_t* offsets, int64_t n,
+                                int64_t num_chunks, const rv_framing* framing_, rv_result** out) {
     if (!out) return fail(RV_ERR_INVALID, "null argument");
     *out = nullptr;
     rv_schema* s = const_cast<rv_schema*>(s_);
     rv_status st = check_decodable(s);
     if (st) return st;
+    st = framing_ok(framing_);
+    if (st) return st;
+    const rv_framing framing = framing_ ? *framing_ : rv_framing{0, 0, -1};
     if (n < 0 || (n > 0 && (!data || !offsets))) return fail(RV_ERR_INVALID, "bad input pointers");
     int device = 0;
     st = ensure_cuda(&device);
@@ -1318,7 +1423,7 @@ rv_status rv_decode_host(const rv_schema* s_, const uint8_t* data, const int64_t
     // pipelining pays when every chunk is big enough to amortise its own launches and copies; many small
     // chunks go through ONE launch that handles all chunks at once
     if (k < 2 || n / k < 16384 || !pipeline_enabled()) {
-        st = decode_host_range(s, data, offsets, 0, n, num_chunks, nullptr, device, out, &h2d, &d2h);
+        st = decode_host_range(s, data, offsets, 0, n, num_chunks, nullptr, device, out, &h2d, &d2h, framing);
         t_timings[4] = h2d;
         t_timings[5] = d2h;
         return st;
@@ -1346,7 +1451,7 @@ rv_status rv_decode_host(const rv_schema* s_, const uint8_t* data, const int64_t
             float hm = 0, dm = 0;
             rv_status rc;
             try {
-                rc = decode_host_range(s, data, offsets, r0, r1, 1, stream, device, &parts[size_t(i)], &hm, &dm);
+                rc = decode_host_range(s, data, offsets, r0, r1, 1, stream, device, &parts[size_t(i)], &hm, &dm, framing);
             } catch (const std::exception& e) {
                 rc = fail(RV_ERR_INVALID, e.what());
             }

@@ -56,6 +56,47 @@ __global__ void compact_kernel(const CompactJob* jobs) {
         for (int64_t i = (nvec << 4) + threadIdx.x; i < job.bytes; i += blockDim.x) job.dst[i] = job.src[i];
 }
 
+// ---- object container files: record offsets -------------------------------------------------------------------------
+// One LANE per block: the datums of a block carry no lengths, so the lane walks them one after the other with the
+// precise COUNT walk (full validation) straight from global memory and notes where each one starts.  Blocks are
+// independent, so a file of thousands of blocks keeps the device busy; the decode kernel then runs on the offsets like
+// on any packed input (the bytes between blocks — count, size, sync marker — trail a block's last record and are ignored
+// like any trailing bytes, fast_decode.rs:825-828).
+__global__ void ocf_offsets_kernel(const OcfParams q) {
+    const int b = int(blockIdx.x * blockDim.x + threadIdx.x);
+    if (b >= q.n_blocks) return;
+    const OcfBlockDev blk = q.blocks[b];
+    uint32_t cur[kMaxStreams];  // the walk's per-stream counters (unused here): local memory
+    long long pos = blk.data_off;
+    const long long end = blk.data_off + blk.size;
+    for (long long i = 0; i < blk.count; ++i) {
+        q.offsets[blk.rec_base + i] = pos;
+        WalkCtx<false> c;
+        c.nodes = q.nodes;
+        c.cur = cur;
+        c.cur_stride = 1;
+        c.sym_off = q.sym_off;
+        c.sym_bytes = q.sym_bytes;
+        c.bufs = nullptr;
+        c.ptrs_saddr = 0;
+        c.err = 0;
+        c.stage_on = false;
+        c.in_range = true;
+        c.row0 = 0;
+        c.store_word = false;
+        c.base = q.data + pos;
+        c.pos = 0;
+        const long long left = end - pos;
+        c.end = uint32_t(left > 0xFFFFFFF0ll ? 0xFFFFFFF0ll : left);
+        InterpWalker::Cur none;
+        InterpWalker::walk<WM_COUNT>(c, q.n_nodes, none);
+        if (c.err) { atomicMin(q.err, (static_cast<unsigned long long>(blk.rec_base + i) << 8) | c.err); return; }
+        pos += c.pos;
+    }
+    if (pos != end) atomicMin(q.err, (static_cast<unsigned long long>(blk.rec_base + (blk.count ? blk.count - 1 : 0)) << 8) | E_FRAME);  // the block's size disagrees with its records
+    if (b == q.n_blocks - 1) q.offsets[q.n_records] = q.end_off;
+}
+
 // ---- multi-GPU gather: every rank pushes its Arrow buffers into the gathered arena on the leader GPU ----------------
 // One launch per rank, blockIdx.x = job, blockIdx.y = part of the job.  The destination is written in aligned 32-bit
 // words, consecutive lanes -> consecutive words (whole 128-byte lines per warp store over NVLink); the fix-up of each
@@ -172,6 +213,11 @@ void launch_fused(const DecodeParams& p, size_t smem, cudaStream_t s) {
 void launch_null_count(const NullCountJob* jobs, int n_jobs, long long* out, cudaStream_t s) {
     if (n_jobs <= 0) return;
     null_count_kernel<<<dim3(n_jobs, 16), 256, 0, s>>>(jobs, out);
+}
+
+void launch_ocf_offsets(const OcfParams& q, cudaStream_t s) {
+    if (q.n_blocks <= 0) return;
+    ocf_offsets_kernel<<<unsigned((q.n_blocks + 63) / 64), 64, 0, s>>>(q);
 }
 
 void launch_gather_push(const PushJob* jobs, int n_jobs, int parts, cudaStream_t s) {

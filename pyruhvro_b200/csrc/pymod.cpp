@@ -99,8 +99,8 @@ struct PinnedPair {  // the two slabs of one call
 PyObject* decode_list(PyObject*, PyObject* args) {
     unsigned long long schema_addr = 0;
     PyObject* list = nullptr;
-    long long num_chunks = 1;
-    if (!PyArg_ParseTuple(args, "KO!L", &schema_addr, &PyList_Type, &list, &num_chunks)) return nullptr;
+    long long num_chunks = 1, header_bytes = 0, check_magic = 0, schema_id = -1;
+    if (!PyArg_ParseTuple(args, "KO!L|LLL", &schema_addr, &PyList_Type, &list, &num_chunks, &header_bytes, &check_magic, &schema_id)) return nullptr;
     const rv_schema* schema = reinterpret_cast<const rv_schema*>(static_cast<uintptr_t>(schema_addr));
     PinnedPair slabs;
     Packed pk;
@@ -115,7 +115,9 @@ PyObject* decode_list(PyObject*, PyObject* args) {
     rv_result* result = nullptr;
     rv_status st = RV_OK;
     Py_BEGIN_ALLOW_THREADS;  // py.detach (src/lib.rs:64-69,82-87): the decode runs without the GIL
-    st = rv_decode_host(schema, reinterpret_cast<const uint8_t*>(pk.data), pk.offsets, pk.n, num_chunks, &result);
+    const rv_framing framing = {int32_t(header_bytes), int32_t(check_magic), int64_t(schema_id)};
+    st = rv_decode_host_framed(schema, reinterpret_cast<const uint8_t*>(pk.data), pk.offsets, pk.n, num_chunks,
+                               header_bytes > 0 ? &framing : nullptr, &result);
     Py_END_ALLOW_THREADS;
     if (st != RV_OK) {
         PyErr_SetString(PyExc_ValueError, rv_last_error());
@@ -141,7 +143,7 @@ PyObject* pack(PyObject*, PyObject* args) {
 }
 
 PyMethodDef methods[] = {
-    {"decode_list", decode_list, METH_VARARGS, "decode_list(schema_handle, records: list[bytes], num_chunks) -> result handle"},
+    {"decode_list", decode_list, METH_VARARGS, "decode_list(schema_handle, records: list[bytes], num_chunks[, header_bytes, check_magic, schema_id]) -> result handle"},
     {"pack", pack, METH_VARARGS, "pack(records: list[bytes]) -> (data, offsets): the packing step alone (test hook)"},
     {nullptr, nullptr, 0, nullptr},
 };
