@@ -17,6 +17,7 @@
 #include <cstring>
 #include <memory>
 #include <thread>
+#include <stdexcept>
 #include <vector>
 
 #include "ruhvro_b200.h"
@@ -111,7 +112,12 @@ PyObject* decode_list(PyObject*, PyObject* args) {
         first = false;
         return p;
     };
-    if (!pack_list(list, alloc, &pk)) return nullptr;
+    try {
+        if (!pack_list(list, alloc, &pk)) return nullptr;
+    } catch (const std::exception& e) {  // bad_alloc, std::system_error from std::thread: a Python error, not an abort
+        PyErr_SetString(PyExc_MemoryError, e.what());
+        return nullptr;
+    }
     rv_result* result = nullptr;
     rv_status st = RV_OK;
     Py_BEGIN_ALLOW_THREADS;  // py.detach (src/lib.rs:64-69,82-87): the decode runs without the GIL
@@ -135,7 +141,13 @@ PyObject* pack(PyObject*, PyObject* args) {
     auto alloc = [&](size_t bytes) -> void* { void* p = std::malloc(bytes ? bytes : 1); blocks.push_back(p); return p; };
     Packed pk;
     PyObject* out = nullptr;
-    if (pack_list(list, alloc, &pk))
+    bool ok = false;
+    try {
+        ok = pack_list(list, alloc, &pk);
+    } catch (const std::exception& e) {
+        PyErr_SetString(PyExc_MemoryError, e.what());
+    }
+    if (ok)
         out = Py_BuildValue("(y#y#)", pk.data, static_cast<Py_ssize_t>(pk.total), reinterpret_cast<const char*>(pk.offsets),
                             static_cast<Py_ssize_t>((static_cast<size_t>(pk.n) + 1) * 8));
     for (void* p : blocks) std::free(p);
