@@ -117,14 +117,33 @@ RV_HD void eof_check(C& c) {
     }
 }
 
-// Bytes 3.. of a varint whose first two bytes both had the continuation bit (rolled: rare in real data, and an
-// unrolled copy at every call site is what made the walkers spill out of the instruction cache).
+// The 7-bit groups of four varint bytes (continuation bits already dropped by the caller's mask) packed into 28 bits.
+RV_HD uint32_t pack7x4(uint32_t w) {
+    return (w & 0x7Fu) | ((w & 0x7F00u) >> 1) | ((w & 0x7F0000u) >> 2) | ((w & 0x7F000000u) >> 3);
+}
+
+// Bytes 3.. of a varint whose first two bytes both had the continuation bit.  FAST flavour on the device: the (at most
+// eight) remaining bytes are taken as ONE 64-bit window — three aligned shared loads — the terminating byte is found
+// with a bit scan and the 7-bit groups are packed without a loop; a byte-at-a-time loop cost ~12 instructions per byte
+// with 64-bit shifts (random longs: ~100 per value).  Elsewhere (precise flavour, host): the reference's loop.
 template <bool CHECK, class C>
 RV_HD uint64_t varint_tail(C& c, uint64_t r) {
-    uint32_t shift = 14;
 #if defined(__CUDA_ARCH__)
-#pragma unroll 1
+    if (C::kShared) {
+        const uint32_t a = c.sbase + c.pos, al = a & ~3u, sh = (a & 3u) * 8u;
+        const uint32_t w0 = lds_u32(al), w1 = lds_u32(al + 4u), w2 = lds_u32(al + 8u);
+        uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+        const uint32_t t_lo = ~lo & 0x80808080u, t_hi = ~hi & 0x80808080u;  // bytes whose continuation bit is clear
+        uint32_t n;                                                       // bytes of this tail, terminator included
+        if (t_lo) { n = uint32_t(__ffs(int(t_lo))) >> 3; lo &= 0xFFFFFFFFu >> (32u - 8u * n); hi = 0u; }
+        else if (t_hi) { n = 4u + (uint32_t(__ffs(int(t_hi))) >> 3); hi &= 0xFFFFFFFFu >> (64u - 8u * n); }
+        else { n = 8u; if (CHECK) c.err |= E_VARINT; }                    // an 11th byte would follow: too long
+        c.pos += n;
+        const uint64_t v56 = uint64_t(pack7x4(lo & 0x7F7F7F7Fu)) | (uint64_t(pack7x4(hi & 0x7F7F7F7Fu)) << 28);
+        return r | (v56 << 14);   // (bits beyond 64 fall off, as in the reference's `<< shift`)
+    }
 #endif
+    uint32_t shift = 14;
     for (;;) {
         const uint32_t b = ld_u8(c, c.pos++);
         r |= uint64_t(b & 0x7Fu) << shift;
