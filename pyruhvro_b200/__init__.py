@@ -53,6 +53,8 @@ class _ArrowArray(ctypes.Structure):
 def _load():
     """Loads the C-ABI library.  Fails loudly: there is no pure-Python or CPU decode path."""
     path = os.path.join(_HERE, "libruhvro_b200.so")
+    if os.environ.get("RV_LIB_PATH"):  # development: a library built with other knobs (tools/tile_sweep.sh)
+        return _bind(ctypes.CDLL(os.environ["RV_LIB_PATH"]))
     # missing or older than its sources: (re)build in-tree, under a file lock, written to a temporary and renamed.
     # Sources absent (a binary-only install) or no compiler: use what is there, fail loudly if nothing is.
     try:
@@ -60,7 +62,10 @@ def _load():
     except Exception:
         if not os.path.exists(path):
             raise
-    L = ctypes.CDLL(path)
+    return _bind(ctypes.CDLL(path))
+
+
+def _bind(L):
     vp, i64, cp = ctypes.c_void_p, ctypes.c_int64, ctypes.c_char_p
     L.rv_schema_parse.argtypes = [cp, ctypes.c_size_t, ctypes.POINTER(vp)]
     L.rv_schema_retain.restype = vp

@@ -131,13 +131,20 @@ RV_HD uint64_t varint_tail(C& c, uint64_t r) {
 #if defined(__CUDA_ARCH__)
     if (C::kShared) {
         const uint32_t a = c.sbase + c.pos, al = a & ~3u, sh = (a & 3u) * 8u;
-        const uint32_t w0 = lds_u32(al), w1 = lds_u32(al + 4u), w2 = lds_u32(al + 8u);
-        uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-        const uint32_t t_lo = ~lo & 0x80808080u, t_hi = ~hi & 0x80808080u;  // bytes whose continuation bit is clear
-        uint32_t n;                                                       // bytes of this tail, terminator included
-        if (t_lo) { n = uint32_t(__ffs(int(t_lo))) >> 3; lo &= 0xFFFFFFFFu >> (32u - 8u * n); hi = 0u; }
-        else if (t_hi) { n = 4u + (uint32_t(__ffs(int(t_hi))) >> 3); hi &= 0xFFFFFFFFu >> (64u - 8u * n); }
-        else { n = 8u; if (CHECK) c.err |= E_VARINT; }                    // an 11th byte would follow: too long
+        const uint32_t w0 = lds_u32(al), w1 = lds_u32(al + 4u);
+        uint32_t lo = __funnelshift_r(w0, w1, sh);
+        const uint32_t t_lo = ~lo & 0x80808080u;                          // bytes whose continuation bit is clear
+        if (t_lo) {                                                       // ends within four more bytes (values below 2^42)
+            const uint32_t n = uint32_t(__ffs(int(t_lo))) >> 3;
+            c.pos += n;
+            lo &= 0xFFFFFFFFu >> (32u - 8u * n);
+            return r | (uint64_t(pack7x4(lo & 0x7F7F7F7Fu)) << 14);
+        }
+        uint32_t hi = __funnelshift_r(w1, lds_u32(al + 8u), sh);
+        const uint32_t t_hi = ~hi & 0x80808080u;
+        uint32_t n = 8u;
+        if (t_hi) { n = 4u + (uint32_t(__ffs(int(t_hi))) >> 3); hi &= 0xFFFFFFFFu >> (64u - 8u * n); }
+        else if (CHECK) c.err |= E_VARINT;                                // an 11th byte would follow: too long
         c.pos += n;
         const uint64_t v56 = uint64_t(pack7x4(lo & 0x7F7F7F7Fu)) | (uint64_t(pack7x4(hi & 0x7F7F7F7Fu)) << 28);
         return r | (v56 << 14);   // (bits beyond 64 fall off, as in the reference's `<< shift`)

@@ -450,11 +450,16 @@ __device__ __forceinline__ void fused_body(const DecodeParams& p, const int tile
         uint32_t* cl = cur + s * kBlock + lane * kPerLane;
         uint32_t v[kPerLane];
         uint32_t any = 0;
+        if constexpr (kPerLane % 4 == 0) {
 #pragma unroll
-        for (int i = 0; i < kPerLane; i += 4) {
-            const uint4 x = *reinterpret_cast<const uint4*>(cl + i);
-            v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
-            any |= x.x | x.y | x.z | x.w;
+            for (int i = 0; i < kPerLane; i += 4) {
+                const uint4 x = *reinterpret_cast<const uint4*>(cl + i);
+                v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
+                any |= x.x | x.y | x.z | x.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kPerLane; ++i) { v[i] = cl[i]; any |= v[i]; }
         }
         uint32_t tile_total;
         // kBlock values below 2^31 / kBlock cannot overflow 31 bits; anything bigger (a tile of huge zero-width
@@ -487,9 +492,14 @@ __device__ __forceinline__ void fused_body(const DecodeParams& p, const int tile
                 if (lane >= d) incl += u;
             }
             const uint32_t base = incl - tot;
+            if constexpr (kPerLane % 4 == 0) {
 #pragma unroll
-            for (int i = 0; i < kPerLane; i += 4)
-                *reinterpret_cast<uint4*>(cl + i) = make_uint4(base + v[i], base + v[i + 1], base + v[i + 2], base + v[i + 3]);
+                for (int i = 0; i < kPerLane; i += 4)
+                    *reinterpret_cast<uint4*>(cl + i) = make_uint4(base + v[i], base + v[i + 1], base + v[i + 2], base + v[i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < kPerLane; ++i) cl[i] = base + v[i];
+            }
             tile_total = __shfl_sync(0xFFFFFFFFu, incl, 31);  // < 2^31 by construction
         }
         // publish right away: the successors' look-backs are waiting for it

@@ -94,7 +94,7 @@ enum ErrCode : uint32_t {
 #define RV_KBLOCK 256
 #endif
 constexpr int kBlock = RV_KBLOCK;  // records per tile == threads per CTA (one record per lane)
-static_assert(kBlock % 128 == 0 && kBlock <= 1024, "tiles are whole groups of 4 warps");
+static_assert(kBlock % 32 == 0 && kBlock >= 64 && kBlock <= 1024, "tiles are whole warps");
 constexpr int kWarps = kBlock / 32;
 
 // Device control block of one decode call, in 64-bit words.
