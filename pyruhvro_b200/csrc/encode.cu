@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <array>
 #include <chrono>
 #include <mutex>
 #include <cstdio>
@@ -56,7 +57,8 @@ struct EncParams {
     int32_t n_nodes;
     const int32_t* sym_off;
     const uint8_t* sym_bytes;
-    int64_t n;            // rows
+    int64_t n;            // rows of this launch (a row group of the batch)
+    int64_t row_base;     // first row of the group inside the batch
     int64_t chunk_rows;
     int32_t k, tiles_per_chunk, n_tiles;
     uint32_t* row_size;   // [n]
@@ -239,8 +241,8 @@ __global__ void __launch_bounds__(kBlock) encode_size_kernel(const EncParams p) 
     EncCtx c;
     enc_init(c, p);
     if (tid < nrec) {
-        enc_range<0, 0>(c, 0, p.n_nodes, r0 + tid);
-        if (c.err) atomicMin(p.err, (static_cast<unsigned long long>(r0 + tid) << 8) | c.err);
+        enc_range<0, 0>(c, 0, p.n_nodes, p.row_base + r0 + tid);
+        if (c.err) atomicMin(p.err, (static_cast<unsigned long long>(p.row_base + r0 + tid) << 8) | c.err);
         p.row_size[r0 + tid] = c.size;
     }
     unsigned long long sum = (tid < nrec) ? c.size : 0u;
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(kBlock) encode_size_kernel(const EncParams p) 
     if (tid == 0) {
         unsigned long long t = 0;
         for (int w = 0; w < kWarps; ++w) t += s_w[w];
-        if (t > 0x7FFFFFFFull) { atomicMin(p.err, (static_cast<unsigned long long>(r0) << 8) | EE_OVERFLOW); t = 0x7FFFFFFFull; }
+        if (t > 0x7FFFFFFFull) { atomicMin(p.err, (static_cast<unsigned long long>(p.row_base + r0) << 8) | EE_OVERFLOW); t = 0x7FFFFFFFull; }
         p.tile_agg[blockIdx.x] = uint32_t(t);
     }
 }
@@ -285,7 +287,7 @@ __global__ void __launch_bounds__(kBlock) encode_write_kernel(const EncParams p)
         EncCtx c;
         enc_init(c, p);
         c.out = staged ? enc_smem + galign + (off - tile_base) : p.out_data[chunk] + off;
-        enc_range<1, 0>(c, 0, p.n_nodes, r0 + tid);
+        enc_range<1, 0>(c, 0, p.n_nodes, p.row_base + r0 + tid);
     }
     if (staged) {
         __syncthreads();
@@ -327,7 +329,7 @@ __global__ void encode_scan_kernel(const EncParams p, unsigned long long* chunk_
         s_part[lane] = w - v;
         if (lane == 31) {
             chunk_tot[j] = w;
-            if (w > 0x7FFFFFFFull) atomicMin(p.err, (static_cast<unsigned long long>(int64_t(j) * p.chunk_rows) << 8) | EE_OVERFLOW);
+            if (w > 0x7FFFFFFFull) atomicMin(p.err, (static_cast<unsigned long long>(p.row_base + int64_t(j) * p.chunk_rows) << 8) | EE_OVERFLOW);
         }
     }
     __syncthreads();
@@ -338,25 +340,37 @@ __global__ void encode_scan_kernel(const EncParams p, unsigned long long* chunk_
 // ------------------------------------------------------------------------------------------------
 // host: plan building from the Arrow C Data structs
 // ------------------------------------------------------------------------------------------------
-struct HostBuf { const void* ptr; size_t bytes; };
+// A host buffer the plan touches, and the byte window [lo, hi) of it that the rows of this launch can address.
+struct HostBuf { const void* ptr; size_t lo, hi; };
 
+// Builds the encode plan for the logical rows [lo, hi) of the batch: every node indexes its Arrow buffers absolutely
+// (row_add), but only the window of each buffer that those rows can reach is recorded for upload — the rows' slice of
+// fixed-width columns, their offsets and the string bytes / child rows between the first and the last offset.  That is
+// what lets a batch be encoded as a few row groups whose uploads, kernels and downloads overlap.
 struct EncBuilder {
     std::vector<ENode> nodes;
     std::vector<int32_t> sym_off;
     std::vector<uint8_t> sym_bytes;
     std::vector<HostBuf> bufs;                 // host buffers to upload
-    std::map<const void*, size_t> buf_index;   // ptr -> index in bufs (sizes are max-merged)
+    std::map<const void*, size_t> buf_index;   // ptr -> index in bufs (windows are merged)
     // per node: indices into bufs for validity / a / b (-1: none)
     std::vector<int> ref_v, ref_a, ref_b;
 
-    int add_buf(const void* p, size_t bytes) {
+    int add_buf(const void* p, size_t lo, size_t hi) {
         if (!p) return -1;
+        if (hi < lo) hi = lo;
         auto it = buf_index.find(p);
-        if (it != buf_index.end()) { bufs[it->second].bytes = std::max(bufs[it->second].bytes, bytes); return int(it->second); }
+        if (it != buf_index.end()) {
+            HostBuf& b = bufs[it->second];
+            if (b.hi == b.lo) { b.lo = lo; b.hi = hi; }
+            else if (hi > lo) { b.lo = std::min(b.lo, lo); b.hi = std::max(b.hi, hi); }
+            return int(it->second);
+        }
         buf_index[p] = bufs.size();
-        bufs.push_back(HostBuf{p, bytes});
+        bufs.push_back(HostBuf{p, lo, hi});
         return int(bufs.size()) - 1;
     }
+    int add_bits(const void* p, int64_t i0, int64_t i1) { return add_buf(p, size_t(i0 >> 3), size_t((i1 + 7) >> 3)); }
     [[noreturn]] static void bad(const std::string& m) { throw std::runtime_error(m); }
 
     static bool fmt_is(const ArrowSchema* s, const char* f) { return std::strcmp(s->format, f) == 0; }
@@ -373,15 +387,17 @@ struct EncBuilder {
     }
 
     // build_field_encoder / build_union_encoder / build_nullable_encoder (fast_encode.rs:191-354).
-    // `base` = slice offset inherited from struct/union ancestors (children of a struct share its rows).
-    void field(const AvroNode& s, const ArrowArray* a, const ArrowSchema* as, int64_t base, int level, int ulevel, int variant, int depth) {
+    // `base` = slice offset inherited from struct/union ancestors (children of a struct share its rows);
+    // [lo, hi) = the logical rows (of the enclosing row space) this launch encodes.
+    void field(const AvroNode& s, const ArrowArray* a, const ArrowSchema* as, int64_t base, int level, int ulevel, int variant, int depth,
+               int64_t lo, int64_t hi) {
         if (s.k == AK::Union) {
             const bool two = s.sub.size() == 2 && (s.sub[0]->k == AK::Null || s.sub[1]->k == AK::Null);
             if (two) {
                 const bool nf = s.sub[0]->k == AK::Null;
                 const AvroNode& inner = nf ? *s.sub[1] : *s.sub[0];
                 if (inner.k == AK::Null || inner.k == AK::Union) bad("fast_encode: unsupported nullable inner type");
-                value(inner, a, as, base, true, nf, level, ulevel, variant, depth);
+                value(inner, a, as, base, true, nf, level, ulevel, variant, depth, lo, hi);
                 return;
             }
             if (!fmt_starts(as, "+us:")) bad("fast_encode: expected (sparse) UnionArray for multi-variant union");
@@ -393,34 +409,34 @@ struct EncBuilder {
             nodes[size_t(id)].row_add = off;
             // sparse union: one buffer (type ids); tolerate the legacy layout with a leading null validity slot
             const void* tids = (a->n_buffers >= 2 && a->buffers[0] == nullptr) ? a->buffers[1] : a->buffers[0];
-            ref_a[size_t(id)] = add_buf(tids, size_t(a->offset + a->length));
+            ref_a[size_t(id)] = add_buf(tids, size_t(off + lo), size_t(off + hi));
             for (size_t i = 0; i < s.sub.size(); ++i)
-                field(*s.sub[i], a->children[i], as->children[i], off, level + 1, ulevel + 1, int(i), depth);
+                field(*s.sub[i], a->children[i], as->children[i], off, level + 1, ulevel + 1, int(i), depth, lo, hi);
             nodes[size_t(id)].end = int32_t(nodes.size());
             return;
         }
-        value(s, a, as, base, false, false, level, ulevel, variant, depth);
+        value(s, a, as, base, false, false, level, ulevel, variant, depth, lo, hi);
     }
 
     void value(const AvroNode& s, const ArrowArray* a, const ArrowSchema* as, int64_t base, bool nullable, bool nf, int level, int ulevel,
-               int variant, int depth) {
+               int variant, int depth, int64_t lo, int64_t hi) {
         const int64_t off = base + a->offset;
-        const size_t rows = size_t(a->offset + a->length);  // buffer extent this array can address
+        const int64_t i0 = off + lo, i1 = off + hi;  // elements of this array's buffers the rows can address
         auto leaf = [&](NodeKind k, const char* what, bool ok, size_t width) {
             if (!ok) bad(std::string("fast_encode: arrow array downcast failed (expected ") + what + ", got format '" + as->format + "')");
             const int id = new_node(k, nullable, nf, level, ulevel, variant);
             nodes[size_t(id)].row_add = off;
             nodes[size_t(id)].end = id + 1;
-            if (nullable) ref_v[size_t(id)] = add_buf(a->buffers[0], (rows + 7) / 8);
-            if (width) ref_a[size_t(id)] = add_buf(a->buffers[1], k == NK_BOOL ? (rows + 7) / 8 : rows * width);
+            if (nullable) ref_v[size_t(id)] = add_bits(a->buffers[0], i0, i1);
+            if (width) ref_a[size_t(id)] = k == NK_BOOL ? add_bits(a->buffers[1], i0, i1) : add_buf(a->buffers[1], size_t(i0) * width, size_t(i1) * width);
             return id;
         };
         auto utf8 = [&](NodeKind k) {
             const int id = leaf(k, "Utf8", fmt_is(as, "u"), 0);
             const int32_t* offs = static_cast<const int32_t*>(a->buffers[1]);
-            ref_a[size_t(id)] = add_buf(offs, (rows + 1) * 4);
-            const size_t data_bytes = offs ? size_t(offs[rows]) : 0;
-            ref_b[size_t(id)] = add_buf(a->buffers[2], data_bytes);
+            ref_a[size_t(id)] = add_buf(offs, size_t(i0) * 4, size_t(i1 + 1) * 4);
+            const size_t d0 = offs ? size_t(offs[i0]) : 0, d1 = offs ? size_t(offs[i1]) : 0;
+            ref_b[size_t(id)] = add_buf(a->buffers[2], d0, d1);
             return id;
         };
         switch (s.k) {
@@ -446,8 +462,8 @@ struct EncBuilder {
                 if (!fmt_is(as, "+s")) bad("fast_encode: expected StructArray for record");
                 const int id = new_node(NK_REC, nullable, nf, level, ulevel, variant);
                 nodes[size_t(id)].row_add = off;
-                if (nullable) ref_v[size_t(id)] = add_buf(a->buffers[0], (rows + 7) / 8);
-                record_children(s, a, as, off, level + 1, ulevel, depth);
+                if (nullable) ref_v[size_t(id)] = add_bits(a->buffers[0], i0, i1);
+                record_children(s, a, as, off, level + 1, ulevel, depth, lo, hi);
                 nodes[size_t(id)].end = int32_t(nodes.size());
                 break;
             }
@@ -457,9 +473,11 @@ struct EncBuilder {
                 if (depth + 1 > kMaxListDepth) bad("arrays/maps nested deeper than " + std::to_string(kMaxListDepth) + " levels are not supported");
                 const int id = new_node(is_map ? NK_MAP : NK_LIST, nullable, nf, level, ulevel, variant);
                 nodes[size_t(id)].row_add = off;
-                if (nullable) ref_v[size_t(id)] = add_buf(a->buffers[0], (rows + 7) / 8);
-                ref_a[size_t(id)] = add_buf(a->buffers[1], (rows + 1) * 4);
+                if (nullable) ref_v[size_t(id)] = add_bits(a->buffers[0], i0, i1);
+                const int32_t* offs = static_cast<const int32_t*>(a->buffers[1]);
+                ref_a[size_t(id)] = add_buf(offs, size_t(i0) * 4, size_t(i1 + 1) * 4);
                 if (a->n_children != 1) bad("fast_encode: list/map without a child");
+                const int64_t c0 = offs ? int64_t(offs[i0]) : 0, c1 = offs ? int64_t(offs[i1]) : 0;  // the rows' items
                 if (is_map) {
                     const ArrowArray* en = a->children[0];
                     const ArrowSchema* ens = as->children[0];
@@ -467,10 +485,10 @@ struct EncBuilder {
                     if (!fmt_is(ens->children[0], "u")) bad("fast_encode: map keys must be StringArray");
                     AvroNode key;
                     key.k = AK::String;
-                    value(key, en->children[0], ens->children[0], en->offset, false, false, level + 1, ulevel, 0xFF, depth + 1);
-                    field(*s.sub[0], en->children[1], ens->children[1], en->offset, level + 1, ulevel, 0xFF, depth + 1);
+                    value(key, en->children[0], ens->children[0], en->offset, false, false, level + 1, ulevel, 0xFF, depth + 1, c0, c1);
+                    field(*s.sub[0], en->children[1], ens->children[1], en->offset, level + 1, ulevel, 0xFF, depth + 1, c0, c1);
                 } else {
-                    field(*s.sub[0], a->children[0], as->children[0], 0, level + 1, ulevel, 0xFF, depth + 1);
+                    field(*s.sub[0], a->children[0], as->children[0], 0, level + 1, ulevel, 0xFF, depth + 1, c0, c1);
                 }
                 nodes[size_t(id)].end = int32_t(nodes.size());
                 break;
@@ -480,7 +498,8 @@ struct EncBuilder {
     }
 
     // build_record_encoder (:153-189): Arrow columns are matched to Avro fields BY NAME
-    void record_children(const AvroNode& rs, const ArrowArray* a, const ArrowSchema* as, int64_t base, int level, int ulevel, int depth) {
+    void record_children(const AvroNode& rs, const ArrowArray* a, const ArrowSchema* as, int64_t base, int level, int ulevel, int depth,
+                         int64_t lo, int64_t hi) {
         for (auto& f : rs.fields) {
             int idx = -1;
             for (int64_t i = 0; i < as->n_children; ++i)
@@ -491,7 +510,7 @@ struct EncBuilder {
                 avail += "]";
                 bad("Arrow struct missing column '" + f.name + "' required by Avro schema. Available columns: " + avail);
             }
-            field(*f.type, a->children[idx], as->children[idx], base, level, ulevel, 0xFF, depth);
+            field(*f.type, a->children[idx], as->children[idx], base, level, ulevel, 0xFF, depth, lo, hi);
         }
     }
 };
@@ -561,128 +580,92 @@ extern "C" int rv_last_encode_timings(float* out_ms, int cap) {
     return n;
 }
 
-rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct ArrowSchema* batch_schema, int64_t num_chunks, rv_encoded** out) {
-    if (!s || !batch || !batch_schema || !out) { rv_set_last_error("null argument"); return RV_ERR_INVALID; }
-    *out = nullptr;
-    struct Releaser {
-        ArrowArray* a; ArrowSchema* s;
-        ~Releaser() { if (a && a->release) a->release(a); if (s && s->release) s->release(s); }
-    } releaser{batch, batch_schema};
-    if (!rv_schema_is_supported(s)) { rv_set_last_error("schema is outside the direct-encode subset; this library has no Value-tree CPU fallback"); return RV_ERR_SCHEMA; }
-    const AvroNode* top = static_cast<const AvroNode*>(rv_schema_avro_root(s));
-    if (std::strcmp(batch_schema->format, "+s") != 0) { rv_set_last_error("fast_encode: expected StructArray"); return RV_ERR_INVALID; }
-    // RV_TRACE=1: phase times of this call on stderr (each mark drains the stream first; development aid)
-    static const bool trace = std::getenv("RV_TRACE") && std::getenv("RV_TRACE")[0] == '1';
-    auto t_prev = std::chrono::steady_clock::now();
-    std::string trace_line;
-    auto mark = [&](const char* what) {
-        if (!trace) return;
-        cudaStreamSynchronize(nullptr);
-        const auto now = std::chrono::steady_clock::now();
-        trace_line += std::string(what) + "=" + std::to_string(std::chrono::duration<double, std::milli>(now - t_prev).count()).substr(0, 6) + "ms ";
-        t_prev = now;
-    };
-    // CUDA-event timings of this call (rv_last_encode_timings): [0] size kernel, [1] scan (+ tile max), [2] write kernel,
-    // [3] upload of the Arrow buffers, [4] download of the datums
+// One row group of the batch — chunks [c0, c1), rows [g0, g1) — on its own stream: upload of the buffer windows its rows
+// reach, size -> scan -> write, download of its chunks.  Returns a status; the message goes to *msg (worker threads have
+// their own thread-local error string).
+static rv_status encode_group(const AvroNode* top, const ArrowArray* batch, const ArrowSchema* batch_schema, int64_t g0, int64_t g1,
+                              int c0, int c1, int64_t chunk_rows, cudaStream_t stream, rv_encoded* res, std::mutex* res_mu, float* ms5,
+                              std::string* msg) {
+#define GRP_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) { *msg = std::string(#expr) + ": " + cudaGetErrorString(e_); cudaStreamSynchronize(stream); (void)cudaGetLastError(); return RV_ERR_CUDA; } \
+    } while (0)
+    EncBuilder b;
+    try {
+        b.record_children(*top, batch, batch_schema, batch->offset, 1, 0, 0, g0, g1);
+    } catch (const std::exception& e) {
+        *msg = e.what();
+        return RV_ERR_INVALID;
+    }
+    const int64_t n = g1 - g0;
+    const int k = c1 - c0;
     struct Ev {
         cudaEvent_t e[8] = {};
         Ev() { for (auto& x : e) if (cudaEventCreate(&x) != cudaSuccess) x = nullptr; }
         ~Ev() { for (auto& x : e) if (x) cudaEventDestroy(x); (void)cudaGetLastError(); }
-        void rec(int i) { if (e[i]) cudaEventRecord(e[i], nullptr); }
+        void rec(int i, cudaStream_t st) { if (e[i]) cudaEventRecord(e[i], st); }
         float ms(int a, int b_) { float t = 0; if (e[a] && e[b_] && cudaEventElapsedTime(&t, e[a], e[b_]) == cudaSuccess) return t; (void)cudaGetLastError(); return 0; }
     } ev;
-    for (float& t : t_enc_timings) t = 0;
-    EncBuilder b;
-    try {
-        b.record_children(*top, batch, batch_schema, batch->offset, 1, 0, 0);
-    } catch (const std::exception& e) {
-        rv_set_last_error(e.what());
-        return RV_ERR_INVALID;
-    }
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { rv_set_last_error("no CUDA device available (this library has no CPU fallback)"); return RV_ERR_CUDA; }
-    const int64_t n = batch->length;
-    const int64_t k64 = clamp_chunks(num_chunks, n);  // serialize.rs:15-17
-    const int k = int(k64);
-    const int64_t chunk_rows = n / k;                 // slice_struct :19-30
-    auto res = std::make_unique<rv_encoded>();
-    res->chunks.resize(size_t(k));
-    for (int j = 0; j < k; ++j) res->chunks[size_t(j)].rows = (j == k - 1) ? n - chunk_rows * (k - 1) : chunk_rows;
 
-    // ---- upload the Arrow buffers the plan touches (one arena) ----
+    // ---- upload the windows of the Arrow buffers this group's rows reach (one device arena) ----
     size_t total = 0;
-    std::vector<size_t> boff(b.bufs.size());
-    for (size_t i = 0; i < b.bufs.size(); ++i) { boff[i] = total; total += (b.bufs[i].bytes + 8 + 63) & ~size_t(63); }
+    std::vector<size_t> boff(b.bufs.size()), blo(b.bufs.size());
+    for (size_t i = 0; i < b.bufs.size(); ++i) {
+        blo[i] = b.bufs[i].lo & ~size_t(63);                 // windows start on a 64-byte boundary of the source buffer
+        boff[i] = total;
+        total += (b.bufs[i].hi - blo[i] + 8 + 63) & ~size_t(63);
+    }
     DevMem d_in, d_nodes, d_symoff, d_symbytes, d_rowsize, d_agg, d_base, d_err, d_tot, d_ptrs;
-    ENC_CUDA(d_in.alloc(total));
-    ev.rec(0);
-    // The caller's Arrow buffers are ordinary pageable memory: copying them to the device directly runs at a
-    // fraction of PCIe speed (the driver stages every piece itself, serially).  Instead a few host threads gather
-    // 16 MiB pieces into one pinned arena (same layout as the device arena) and each piece's H2D copy is issued as
-    // soon as it has landed, so the gather of piece i+1 overlaps the DMA of piece i.
-    mark("plan");
-    std::shared_ptr<void> h_in_keep;
-    // (buffers that already live in pinned / registered memory — e.g. batches this library decoded — go direct)
+    GRP_CUDA(d_in.alloc(total));
+    ev.rec(0, stream);
+    // Buffers in ordinary pageable memory are staged through a pinned arena in 16 MiB pieces (a direct copy runs at a
+    // fraction of PCIe speed); pinned / registered buffers — e.g. batches this library decoded — go direct.
     bool pageable = false;
     for (size_t i = 0; i < b.bufs.size() && !pageable; ++i) {
-        if (b.bufs[i].bytes < (size_t(1) << 20)) continue;
+        if (b.bufs[i].hi - blo[i] < (size_t(1) << 20)) continue;
         cudaPointerAttributes at{};
         if (cudaPointerGetAttributes(&at, b.bufs[i].ptr) != cudaSuccess) { (void)cudaGetLastError(); pageable = true; }
         else pageable = at.type == cudaMemoryTypeUnregistered;
     }
+    std::shared_ptr<void> h_in_keep;
+    uint8_t* h_in = nullptr;
     if (pageable && total >= (size_t(4) << 20)) {
-        uint8_t* h_in = static_cast<uint8_t*>(rv_host_alloc(total));
-        if (!h_in) return RV_ERR_CUDA;
+        h_in = static_cast<uint8_t*>(rv_host_alloc(total));
+        if (!h_in) { *msg = "pinned staging allocation failed"; return RV_ERR_CUDA; }
         h_in_keep = std::shared_ptr<void>(h_in, [](void* q) { rv_host_free(q); });
-        struct Piece { const uint8_t* src; size_t off, len; };
-        std::vector<Piece> pieces;
-        const size_t kPiece = size_t(16) << 20;
-        for (size_t i = 0; i < b.bufs.size(); ++i)
-            for (size_t o = 0; o < b.bufs[i].bytes; o += kPiece)
-                pieces.push_back(Piece{static_cast<const uint8_t*>(b.bufs[i].ptr) + o, boff[i] + o, std::min(kPiece, b.bufs[i].bytes - o)});
-        int device = 0;
-        ENC_CUDA(cudaGetDevice(&device));
-        std::atomic<size_t> next{0};
-        std::atomic<int> failed{0};
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const size_t n_threads = std::min<size_t>(std::min<size_t>(16, hw), pieces.size());
-        uint8_t* d_base_in = static_cast<uint8_t*>(d_in.p);
-        auto work = [&]() {
-            if (cudaSetDevice(device) != cudaSuccess) { failed.store(1); return; }
-            for (size_t i; (i = next.fetch_add(1)) < pieces.size();) {
-                const Piece& pc = pieces[i];
-                std::memcpy(h_in + pc.off, pc.src, pc.len);
-                if (cudaMemcpyAsync(d_base_in + pc.off, h_in + pc.off, pc.len, cudaMemcpyHostToDevice, nullptr) != cudaSuccess) failed.store(1);
-            }
-        };
-        std::vector<std::thread> pool;
-        for (size_t t = 1; t < n_threads; ++t) pool.emplace_back(work);
-        work();
-        for (auto& t : pool) t.join();
-        if (failed.load()) { (void)cudaGetLastError(); rv_set_last_error("staged upload of the Arrow buffers failed"); return RV_ERR_CUDA; }
-    } else {
-        for (size_t i = 0; i < b.bufs.size(); ++i)
-            if (b.bufs[i].bytes) ENC_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(d_in.p) + boff[i], b.bufs[i].ptr, b.bufs[i].bytes, cudaMemcpyHostToDevice, nullptr));
+    }
+    const size_t kPiece = size_t(16) << 20;
+    for (size_t i = 0; i < b.bufs.size(); ++i) {
+        const uint8_t* src = static_cast<const uint8_t*>(b.bufs[i].ptr) + blo[i];
+        const size_t bytes = b.bufs[i].hi - blo[i];
+        uint8_t* dst = static_cast<uint8_t*>(d_in.p) + boff[i];
+        for (size_t o = 0; o < bytes; o += kPiece) {
+            const size_t len = std::min(kPiece, bytes - o);
+            const uint8_t* from = src + o;
+            if (h_in) { std::memcpy(h_in + boff[i] + o, from, len); from = h_in + boff[i] + o; }
+            GRP_CUDA(cudaMemcpyAsync(dst + o, from, len, cudaMemcpyHostToDevice, stream));
+        }
     }
     for (size_t i = 0; i < b.nodes.size(); ++i) {
-        auto fix = [&](int ref) -> const uint8_t* { return ref < 0 ? nullptr : static_cast<const uint8_t*>(d_in.p) + boff[size_t(ref)]; };
+        // device address of the buffer's byte 0 (the window starts at byte blo): nodes keep indexing absolutely
+        auto fix = [&](int ref) -> const uint8_t* { return ref < 0 ? nullptr : static_cast<const uint8_t*>(d_in.p) + boff[size_t(ref)] - blo[size_t(ref)]; };
         b.nodes[i].validity = fix(b.ref_v[i]);
         b.nodes[i].buf_a = fix(b.ref_a[i]);
         b.nodes[i].buf_b = fix(b.ref_b[i]);
     }
-    ENC_CUDA(d_nodes.alloc(b.nodes.size() * sizeof(ENode)));
-    ENC_CUDA(cudaMemcpyAsync(d_nodes.p, b.nodes.data(), b.nodes.size() * sizeof(ENode), cudaMemcpyHostToDevice, nullptr));
-    ENC_CUDA(d_symoff.alloc(b.sym_off.size() * 4));
-    ENC_CUDA(d_symbytes.alloc(b.sym_bytes.size()));
-    if (!b.sym_off.empty()) ENC_CUDA(cudaMemcpyAsync(d_symoff.p, b.sym_off.data(), b.sym_off.size() * 4, cudaMemcpyHostToDevice, nullptr));
-    if (!b.sym_bytes.empty()) ENC_CUDA(cudaMemcpyAsync(d_symbytes.p, b.sym_bytes.data(), b.sym_bytes.size(), cudaMemcpyHostToDevice, nullptr));
+    GRP_CUDA(d_nodes.alloc(b.nodes.size() * sizeof(ENode)));
+    GRP_CUDA(cudaMemcpyAsync(d_nodes.p, b.nodes.data(), b.nodes.size() * sizeof(ENode), cudaMemcpyHostToDevice, stream));
+    GRP_CUDA(d_symoff.alloc(b.sym_off.size() * 4));
+    GRP_CUDA(d_symbytes.alloc(b.sym_bytes.size()));
+    if (!b.sym_off.empty()) GRP_CUDA(cudaMemcpyAsync(d_symoff.p, b.sym_off.data(), b.sym_off.size() * 4, cudaMemcpyHostToDevice, stream));
+    if (!b.sym_bytes.empty()) GRP_CUDA(cudaMemcpyAsync(d_symbytes.p, b.sym_bytes.data(), b.sym_bytes.size(), cudaMemcpyHostToDevice, stream));
+    ev.rec(1, stream);
 
-    ev.rec(1);
-    mark("upload");
     EncParams p{};
     p.nodes = static_cast<const ENode*>(d_nodes.p); p.n_nodes = int32_t(b.nodes.size());
     p.sym_off = static_cast<const int32_t*>(d_symoff.p); p.sym_bytes = static_cast<const uint8_t*>(d_symbytes.p);
-    p.n = n; p.chunk_rows = chunk_rows; p.k = k;
+    p.n = n; p.row_base = g0; p.chunk_rows = chunk_rows; p.k = k;
     const int64_t tpc = std::max<int64_t>(1, (chunk_rows + kBlock - 1) / kBlock);
     const int64_t last_rows = n - chunk_rows * (k - 1);
     const int64_t n_tiles = n > 0 ? tpc * (k - 1) + (last_rows + kBlock - 1) / kBlock : 0;
@@ -690,35 +673,34 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
     std::vector<unsigned long long> chunk_tot(static_cast<size_t>(k), 0ull);
     unsigned long long max_tile = 0;
     if (n > 0) {
-        ENC_CUDA(d_rowsize.alloc(size_t(n) * 4));
-        ENC_CUDA(d_agg.alloc(size_t(n_tiles) * 4));
-        ENC_CUDA(d_base.alloc(size_t(n_tiles) * 4));
-        ENC_CUDA(d_err.alloc(16));
-        ENC_CUDA(d_tot.alloc(size_t(k) * 8));
-        ENC_CUDA(cudaMemsetAsync(d_err.p, 0xFF, 8, nullptr));
+        GRP_CUDA(d_rowsize.alloc(size_t(n) * 4));
+        GRP_CUDA(d_agg.alloc(size_t(n_tiles) * 4));
+        GRP_CUDA(d_base.alloc(size_t(n_tiles) * 4));
+        GRP_CUDA(d_err.alloc(16));
+        GRP_CUDA(d_tot.alloc(size_t(k) * 8));
+        GRP_CUDA(cudaMemsetAsync(d_err.p, 0xFF, 8, stream));
         p.row_size = static_cast<uint32_t*>(d_rowsize.p); p.tile_agg = static_cast<uint32_t*>(d_agg.p);
         p.tile_base = static_cast<uint32_t*>(d_base.p); p.err = static_cast<unsigned long long*>(d_err.p);
-        encode_size_kernel<<<unsigned(n_tiles), kBlock>>>(p);
-        ev.rec(2);
+        encode_size_kernel<<<unsigned(n_tiles), kBlock, 0, stream>>>(p);
+        ev.rec(2, stream);
         int thr = 32;
         while (thr < 1024 && thr < tpc) thr <<= 1;
-        encode_scan_kernel<<<unsigned(k), thr>>>(p, static_cast<unsigned long long*>(d_tot.p));
-        ENC_CUDA(cudaMemsetAsync(static_cast<uint8_t*>(d_err.p) + 8, 0, 8, nullptr));
-        encode_tile_max_kernel<<<std::max(1, std::min(int((n_tiles + 255) / 256), 592)), 256>>>(p, static_cast<unsigned long long*>(d_err.p) + 1);
-        ENC_CUDA(cudaGetLastError());
-        ev.rec(3);
+        encode_scan_kernel<<<unsigned(k), thr, 0, stream>>>(p, static_cast<unsigned long long*>(d_tot.p));
+        GRP_CUDA(cudaMemsetAsync(static_cast<uint8_t*>(d_err.p) + 8, 0, 8, stream));
+        encode_tile_max_kernel<<<std::max(1, std::min(int((n_tiles + 255) / 256), 592)), 256, 0, stream>>>(p, static_cast<unsigned long long*>(d_err.p) + 1);
+        GRP_CUDA(cudaGetLastError());
+        ev.rec(3, stream);
         unsigned long long err_word = ~0ull;
-        ENC_CUDA(cudaMemcpyAsync(&max_tile, static_cast<uint8_t*>(d_err.p) + 8, 8, cudaMemcpyDeviceToHost, nullptr));
-        ENC_CUDA(cudaMemcpyAsync(&err_word, d_err.p, 8, cudaMemcpyDeviceToHost, nullptr));
-        ENC_CUDA(cudaMemcpyAsync(chunk_tot.data(), d_tot.p, size_t(k) * 8, cudaMemcpyDeviceToHost, nullptr));
-        ENC_CUDA(cudaStreamSynchronize(nullptr));
-        mark("size+scan");
+        GRP_CUDA(cudaMemcpyAsync(&max_tile, static_cast<uint8_t*>(d_err.p) + 8, 8, cudaMemcpyDeviceToHost, stream));
+        GRP_CUDA(cudaMemcpyAsync(&err_word, d_err.p, 8, cudaMemcpyDeviceToHost, stream));
+        GRP_CUDA(cudaMemcpyAsync(chunk_tot.data(), d_tot.p, size_t(k) * 8, cudaMemcpyDeviceToHost, stream));
+        GRP_CUDA(cudaStreamSynchronize(stream));
         if (err_word != ~0ull) {
             const uint32_t code = uint32_t(err_word & 0xFF);
             const std::string what = code == EE_ENUM ? "fast_encode: enum symbol not in schema"
                                      : code == EE_BRANCH ? "fast_encode: union type_id out of range"
                                                          : "Arrow i32 offset overflow: a chunk's datums exceed 2 GiB";
-            rv_set_last_error((what + " (row " + std::to_string(err_word >> 8) + ")").c_str());
+            *msg = what + " (row " + std::to_string(err_word >> 8) + ")";
             return rv_status(code);
         }
     }
@@ -728,18 +710,18 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
     std::vector<int32_t*> h_offs(static_cast<size_t>(k), nullptr);
     std::vector<size_t> off_bytes(static_cast<size_t>(k), 0);
     for (int j = 0; j < k; ++j) {
-        auto& c = res->chunks[size_t(j)];
+        auto& c = res->chunks[size_t(c0 + j)];
         c.data_bytes = int64_t(chunk_tot[size_t(j)]);
         off_bytes[size_t(j)] = (size_t(c.rows + 1) * 4 + 63) & ~size_t(63);
-        ENC_CUDA(d_out[size_t(j)].alloc(off_bytes[size_t(j)] + size_t(c.data_bytes) + 64));
+        GRP_CUDA(d_out[size_t(j)].alloc(off_bytes[size_t(j)] + size_t(c.data_bytes) + 64));
         h_offs[size_t(j)] = static_cast<int32_t*>(d_out[size_t(j)].p);
         h_data[size_t(j)] = static_cast<uint8_t*>(d_out[size_t(j)].p) + off_bytes[size_t(j)];
-        if (c.rows == 0) ENC_CUDA(cudaMemsetAsync(d_out[size_t(j)].p, 0, 64, nullptr));
+        if (c.rows == 0) GRP_CUDA(cudaMemsetAsync(d_out[size_t(j)].p, 0, 64, stream));
     }
     if (n > 0) {
-        ENC_CUDA(d_ptrs.alloc(size_t(k) * 16));
-        ENC_CUDA(cudaMemcpyAsync(d_ptrs.p, h_data.data(), size_t(k) * 8, cudaMemcpyHostToDevice, nullptr));
-        ENC_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(d_ptrs.p) + size_t(k) * 8, h_offs.data(), size_t(k) * 8, cudaMemcpyHostToDevice, nullptr));
+        GRP_CUDA(d_ptrs.alloc(size_t(k) * 16));
+        GRP_CUDA(cudaMemcpyAsync(d_ptrs.p, h_data.data(), size_t(k) * 8, cudaMemcpyHostToDevice, stream));
+        GRP_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(d_ptrs.p) + size_t(k) * 8, h_offs.data(), size_t(k) * 8, cudaMemcpyHostToDevice, stream));
         p.out_data = static_cast<uint8_t* const*>(d_ptrs.p);
         p.out_offsets = reinterpret_cast<int32_t* const*>(static_cast<uint8_t*>(d_ptrs.p) + size_t(k) * 8);
         // staging area: the largest tile (+ alignment), capped so at least two CTAs share an SM
@@ -749,40 +731,103 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
             static std::mutex attr_mu;
             static std::vector<char> attr_set;
             int dev_now = 0;
-            ENC_CUDA(cudaGetDevice(&dev_now));
+            GRP_CUDA(cudaGetDevice(&dev_now));
             std::lock_guard<std::mutex> g(attr_mu);
             if (attr_set.size() <= size_t(dev_now)) attr_set.resize(size_t(dev_now) + 1, 0);
             if (!attr_set[size_t(dev_now)]) {
-                ENC_CUDA(cudaFuncSetAttribute(encode_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-                ENC_CUDA(cudaFuncSetAttribute(encode_write_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                GRP_CUDA(cudaFuncSetAttribute(encode_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+                GRP_CUDA(cudaFuncSetAttribute(encode_write_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
                 attr_set[size_t(dev_now)] = 1;
             }
         }
         p.stage_cap = uint32_t(stage);
-        mark("alloc_out");
-        ev.rec(4);
-        encode_write_kernel<<<unsigned(n_tiles), kBlock, stage>>>(p);
-        ev.rec(5);
-        ENC_CUDA(cudaGetLastError());
-        mark("write");
+        ev.rec(4, stream);
+        encode_write_kernel<<<unsigned(n_tiles), kBlock, stage, stream>>>(p);
+        ev.rec(5, stream);
+        GRP_CUDA(cudaGetLastError());
     }
-    ev.rec(6);
+    ev.rec(6, stream);
     for (int j = 0; j < k; ++j) {
-        auto& c = res->chunks[size_t(j)];
+        auto& c = res->chunks[size_t(c0 + j)];
         const size_t bytes = off_bytes[size_t(j)] + size_t(c.data_bytes);
         void* h = rv_host_alloc(bytes + 64);
-        if (!h) return RV_ERR_CUDA;
-        res->keep.emplace_back(h, [](void* q) { rv_host_free(q); });
+        if (!h) { *msg = "pinned allocation of an output chunk failed"; cudaStreamSynchronize(stream); return RV_ERR_CUDA; }
+        {
+            std::lock_guard<std::mutex> g(*res_mu);
+            res->keep.emplace_back(h, [](void* q) { rv_host_free(q); });
+        }
         c.host = h;
-        ENC_CUDA(cudaMemcpyAsync(h, d_out[size_t(j)].p, bytes, cudaMemcpyDeviceToHost, nullptr));
+        GRP_CUDA(cudaMemcpyAsync(h, d_out[size_t(j)].p, bytes, cudaMemcpyDeviceToHost, stream));
     }
-    ev.rec(7);
-    ENC_CUDA(cudaStreamSynchronize(nullptr));
-    t_enc_timings[3] = ev.ms(0, 1);
-    t_enc_timings[4] = ev.ms(6, 7);
-    if (n > 0) { t_enc_timings[0] = ev.ms(1, 2); t_enc_timings[1] = ev.ms(2, 3); t_enc_timings[2] = ev.ms(4, 5); }
-    mark("download");
-    if (trace) std::fprintf(stderr, "[rv trace encode] %s\n", trace_line.c_str());
+    ev.rec(7, stream);
+    GRP_CUDA(cudaStreamSynchronize(stream));
+    ms5[3] = ev.ms(0, 1);
+    ms5[4] = ev.ms(6, 7);
+    if (n > 0) { ms5[0] = ev.ms(1, 2); ms5[1] = ev.ms(2, 3); ms5[2] = ev.ms(4, 5); }
+    return RV_OK;
+#undef GRP_CUDA
+}
+
+rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct ArrowSchema* batch_schema, int64_t num_chunks, rv_encoded** out) {
+    if (!s || !batch || !batch_schema || !out) { rv_set_last_error("null argument"); return RV_ERR_INVALID; }
+    *out = nullptr;
+    struct Releaser {  // ownership of the C structs moved to us
+        ArrowArray* a; ArrowSchema* s;
+        ~Releaser() { if (a && a->release) a->release(a); if (s && s->release) s->release(s); }
+    } releaser{batch, batch_schema};
+    if (!rv_schema_is_supported(s)) { rv_set_last_error("schema is outside the direct-encode subset; this library has no Value-tree CPU fallback"); return RV_ERR_SCHEMA; }
+    const AvroNode* top = static_cast<const AvroNode*>(rv_schema_avro_root(s));
+    if (std::strcmp(batch_schema->format, "+s") != 0) { rv_set_last_error("fast_encode: expected StructArray"); return RV_ERR_INVALID; }
+    for (float& t : t_enc_timings) t = 0;
+    {   // plan errors (missing column, wrong Arrow type, ...) surface before any GPU work, on the calling thread
+        EncBuilder probe;
+        try {
+            probe.record_children(*top, batch, batch_schema, batch->offset, 1, 0, 0, 0, 0);
+        } catch (const std::exception& e) {
+            rv_set_last_error(e.what());
+            return RV_ERR_INVALID;
+        }
+    }
+    int ndev = 0, device = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { rv_set_last_error("no CUDA device available (this library has no CPU fallback)"); return RV_ERR_CUDA; }
+    ENC_CUDA(cudaGetDevice(&device));
+    const int64_t n = batch->length;
+    const int64_t k64 = clamp_chunks(num_chunks, n);  // serialize.rs:15-17
+    const int k = int(k64);
+    const int64_t chunk_rows = n / k;                 // slice_struct :19-30
+    auto res = std::make_unique<rv_encoded>();
+    res->chunks.resize(size_t(k));
+    for (int j = 0; j < k; ++j) res->chunks[size_t(j)].rows = (j == k - 1) ? n - chunk_rows * (k - 1) : chunk_rows;
+
+    // Row groups of whole chunks, each on its own stream and host thread: the upload of group g+1 overlaps the kernels
+    // and the download of group g (full-duplex PCIe), like the decode side's chunk pipeline.  Small batches: one group.
+    int groups = 1;
+    if (k >= 2 && n >= (int64_t(1) << 18)) groups = std::min(k, 4);
+    if (const char* e = std::getenv("RV_ENC_GROUPS")) groups = std::max(1, std::min(k, std::atoi(e)));
+    std::vector<rv_status> status(size_t(groups), RV_OK);
+    std::vector<std::string> message(static_cast<size_t>(groups));
+    std::vector<std::array<float, 5>> times(static_cast<size_t>(groups), std::array<float, 5>{0, 0, 0, 0, 0});
+    std::mutex res_mu;
+    auto run = [&](int g) {
+        cudaSetDevice(device);
+        const int c0 = int(int64_t(g) * k / groups), c1 = int(int64_t(g + 1) * k / groups);
+        const int64_t g0 = int64_t(c0) * chunk_rows, g1 = (c1 == k) ? n : int64_t(c1) * chunk_rows;
+        cudaStream_t stream = nullptr;
+        if (groups > 1 && cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) { status[size_t(g)] = RV_ERR_CUDA; message[size_t(g)] = "stream creation failed"; return; }
+        status[size_t(g)] = encode_group(top, batch, batch_schema, g0, g1, c0, c1, chunk_rows, stream, res.get(), &res_mu, times[size_t(g)].data(), &message[size_t(g)]);
+        if (stream) cudaStreamDestroy(stream);
+    };
+    if (groups == 1) run(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int g = 1; g < groups; ++g) pool.emplace_back(run, g);
+        run(0);
+        for (auto& t : pool) t.join();
+    }
+    for (int g = 0; g < groups; ++g) {
+        if (status[size_t(g)] != RV_OK) { rv_set_last_error(message[size_t(g)].c_str()); return status[size_t(g)]; }  // lowest rows first
+        for (int q = 0; q < 5; ++q) t_enc_timings[q] += times[size_t(g)][size_t(q)];
+    }
     *out = res.release();
     return RV_OK;
 }
