@@ -213,9 +213,15 @@ def _export_batches(result_handle: int, schema: Schema) -> List[pa.RecordBatch]:
         lib.rv_result_free(result_handle)
 
 
+_native_mod = None
+
+
 def _ext():
-    import importlib
-    return importlib.import_module(__name__ + "._native")  # built by _build.build_ext(); ImportError is the loud failure
+    global _native_mod
+    if _native_mod is None:
+        import importlib
+        _native_mod = importlib.import_module(__name__ + "._native")  # built by _build.build_ext(); ImportError is the loud failure
+    return _native_mod
 
 
 class Framing(ctypes.Structure):
