@@ -719,15 +719,25 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
     auto rows_of = [&](int j) { return j == k - 1 ? last_rows : chunk_rows; };
     std::vector<unsigned long long> caps(chunk_tot.size(), 0ull);
     bool exact_caps = false;
+    bool count_only = !stats.valid;
     if (stats.valid) {
         const double margin = env_double("RV_CAP_MARGIN", 1.10);
+        // What the input can possibly hold bounds the plan (history from a batch of a few huge records must not size the
+        // buffers of a batch of millions): every string byte and every list item costs at least one input byte.
+        const double in_bytes = hints.total_bytes >= 0 ? double(hints.total_bytes) : double(n) * stats.in_per_row * 2.0 + 65536.0;
+        double planned = 0;
         for (int j = 0; j < k; ++j)
             for (int i = 0; i < S; ++i) {
-                const double want = double(rows_of(j)) * stats.per_row[size_t(i)] * margin + 4096.0;
+                double want = double(rows_of(j)) * stats.per_row[size_t(i)] * margin + 4096.0;
+                const Stream& st_ = plan.streams[size_t(i)];
+                const bool enum_text = !st_.is_rows && plan.nodes[size_t(st_.node)].kind == NK_ENUM;  // symbol text is not input bytes
+                if (!enum_text) want = std::min(want, in_bytes + 4096.0);
                 caps[size_t(j) * size_t(Sx) + size_t(i)] = static_cast<unsigned long long>(std::min(want, 2147483647.0));
+                planned += want;
             }
+        // a plan far beyond anything the input could produce (stale history): measure first instead
+        if (planned > 64.0 * in_bytes + double(size_t(1) << 30)) count_only = true;
     }
-    bool count_only = !stats.valid;
     Layout capL;
     std::vector<long long> ones(ones_n, 0);
     unsigned long long* hb_ctrl = reinterpret_cast<unsigned long long*>(h_back + off_ctrl);
@@ -742,9 +752,13 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
             arena_sp->drop_device();
             arena_sp->bytes = capL.total_bytes;
             arena_sp->dev = devmem().get(std::max<size_t>(capL.total_bytes, 64), device, &arena_sp->dev_actual);
-            if (!arena_sp->dev)
-                return fail(RV_ERR_CUDA, "device allocation of the Arrow buffer arena failed (" + std::to_string(capL.total_bytes) + " bytes)");
-            arena = static_cast<uint8_t*>(arena_sp->dev);
+            if (!arena_sp->dev) {
+                // the planned arena does not fit: measure, then allocate exactly what the data needs
+                if (!exact_caps) { count_only = true; }
+                else return fail(RV_ERR_CUDA, "device allocation of the Arrow buffer arena failed (" + std::to_string(capL.total_bytes) + " bytes)");
+            } else {
+                arena = static_cast<uint8_t*>(arena_sp->dev);
+            }
         }
         // ---- template of the call state
         std::memset(h_misc, 0, misc_bytes);

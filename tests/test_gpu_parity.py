@@ -294,6 +294,24 @@ def test_capacity_plan_measures_first_then_runs_one_pass_and_repeats_when_outgro
     assert pr.lib.rv_last_passes() == 1
 
 
+def test_capacity_plan_is_bounded_by_what_the_input_can_hold(coracle):
+    """History from a batch of a few huge records must not size the buffers of a batch of many small ones (the plan is
+    capped by the input's bytes), and the other way round the data simply outgrows the plan and the pass repeats."""
+    sj = '{"type":"record","name":"H","fields":[{"name":"s","type":"string"},{"name":"xs","type":{"type":"array","items":"string"}}]}'
+    s = po.parse_schema(sj)
+    schema = pr._get_or_parse_schema(sj)
+    pr.lib.rv_schema_forget_stats(schema.handle)
+    big = [po.encode_datum(s, {"s": "x" * 3_000_000, "xs": ["y" * 1_000_000] * 3}) for _ in range(3)]
+    data, off = po.pack_records(big)
+    assert_matches_oracle(coracle, pr.decode_packed(data, off, 3, sj, 1), sj, data, off, 3, 1)
+    small = [po.encode_datum(s, {"s": "ab", "xs": ["c"]}) for _ in range(400_000)]
+    data, off = po.pack_records(small)
+    got = pr.decode_packed(data, off, len(small), sj, 2)          # 400 k rows x 6 MB/row of history would be terabytes
+    assert_matches_oracle(coracle, got, sj, data, off, len(small), 2, full_validate=False)
+    data, off = po.pack_records(big)
+    assert_matches_oracle(coracle, pr.decode_packed(data, off, 3, sj, 1), sj, data, off, 3, 1)
+
+
 @pytest.mark.parametrize("name,n,k", [("kafka", 10_000_000, 8), ("flat", 2_000_000, 8), ("wide", 2_000_000, 8)])
 def test_bench_scale_parity(coracle, name, n, k):
     """The configurations bench.py times (C3 at 10 M records / 8 chunks; C2 and C4 at 2 M), every exported buffer of

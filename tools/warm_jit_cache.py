@@ -25,6 +25,7 @@ def schemas():
                '{"name":"m","type":{"type":"map","values":{"type":"array","items":{"type":"array","items":["null","string"]}}}}]}')
     out.append('{"type":"record","name":"C","fields":[{"name":"id","type":"long"},{"name":"s","type":["null","string"]},'
                '{"name":"xs","type":{"type":"array","items":"int"}}]}')
+    out.append('{"type":"record","name":"H","fields":[{"name":"s","type":"string"},{"name":"xs","type":{"type":"array","items":"string"}}]}')
     from tests.parity import gen_case_wide
     from tests.test_wide_types import ALL_WIDE
     out.append(ALL_WIDE)
