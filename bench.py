@@ -321,10 +321,20 @@ class Bench:
         if sampler:
             sampler.active.clear()
         self.barrier()
+        my_ms = 1000.0 * s / steps
         s = self.max_over_ranks(s)
         idx = 8 * (w["n"] + 1)
         h2d_b, d2h_b = w["total_in"] + idx, buffer_bytes
-        return {"ms_per_step": 1000.0 * s / steps, "h2d_bytes": h2d_b, "d2h_bytes": d2h_b,
+        per_rank = None
+        if self.world > 1:  # every rank's own step time and copy-engine rates (NUMA placement shows up here)
+            import torch.distributed as dist
+            mine = self.torch.tensor([my_ms, h2d_b / max(h2d_ms / steps, 1e-9) / 1e6, d2h_b / max(d2h_ms / steps, 1e-9) / 1e6],
+                                     dtype=self.torch.float64, device=self.dev)
+            allv = [self.torch.zeros_like(mine) for _ in range(self.world)]
+            dist.all_gather(allv, mine)
+            per_rank = [{"rank": r, "ms_per_step": float(v[0]), "h2d_gbs_while_copying": float(v[1]), "d2h_gbs_while_copying": float(v[2])}
+                        for r, v in enumerate(allv)]
+        return {"ms_per_step": 1000.0 * s / steps, "h2d_bytes": h2d_b, "d2h_bytes": d2h_b, "per_rank": per_rank,
                 # copy-engine time summed over the call's chunks (they overlap each other and the kernels)
                 "h2d_busy_ms": h2d_ms / steps, "d2h_busy_ms": d2h_ms / steps,
                 "h2d_gbs_while_copying": h2d_b / max(h2d_ms / steps, 1e-9) / 1e6, "d2h_gbs_while_copying": d2h_b / max(d2h_ms / steps, 1e-9) / 1e6}
@@ -549,6 +559,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host_res["h2d_bytes"], "d2h_bytes_per_step": host_res["d2h_bytes"],
                 "ms_per_step": host_res["ms_per_step"], "h2d_busy_ms": host_res["h2d_busy_ms"], "d2h_busy_ms": host_res["d2h_busy_ms"],
                 "h2d_gbs_while_copying": host_res["h2d_gbs_while_copying"], "d2h_gbs_while_copying": host_res["d2h_gbs_while_copying"],
+                "per_rank": host_res["per_rank"],
                 "path": "rv_decode_host: pinned host Avro in -> pinned host Arrow out, chunks pipelined on persistent NUMA-bound workers"},
         "gpu_launches": dev_res["launches"],
         "roofline": rl,
