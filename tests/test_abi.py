@@ -244,3 +244,27 @@ def test_list_packing_matches_binaryarray_from_vec():
         ext.pack([b"a", "b"])
     with pytest.raises(TypeError):
         ext.pack((b"a",))                                              # a list, like PyO3's Vec<Bound<PyBytes>> extraction
+
+
+def test_framed_entry_points_validate_before_touching_the_gpu():
+    """Argument and container errors of the framed adapters are host-side: they surface without a CUDA device."""
+    import numpy as np
+    sj = '{"type":"record","name":"R","fields":[{"name":"x","type":"int"}]}'
+    data, off = np.zeros(8, dtype=np.uint8), np.array([0, 8], dtype=np.int64)
+    with pytest.raises(ValueError, match="header_bytes >= 5"):
+        pr.decode_packed(data, off, 1, sj, 1, framing=pr.Framing(3, 1, -1))
+    with pytest.raises(ValueError, match="out of range"):
+        pr.decode_packed(data, off, 1, sj, 1, framing=pr.Framing(-1, 0, -1))
+    with pytest.raises(ValueError, match="magic"):
+        pr.deserialize_ocf(b"not an object container file", 1)
+    header = b"Obj\x01" + po.zigzag_bytes(1) + po.zigzag_bytes(11) + b"avro.schema" + po.zigzag_bytes(len(sj)) + sj.encode() + po.zigzag_bytes(0)
+    with pytest.raises(ValueError, match="sync"):
+        pr.deserialize_ocf(header + bytes(8), 1)                                   # truncated sync marker
+    sync = bytes(range(16))
+    with pytest.raises(ValueError, match="truncated block"):
+        pr.deserialize_ocf(header + sync + po.zigzag_bytes(3) + po.zigzag_bytes(100) + b"\x02", 1)
+    with pytest.raises(ValueError, match="sync marker mismatch"):
+        pr.deserialize_ocf(header + sync + po.zigzag_bytes(1) + po.zigzag_bytes(1) + b"\x02" + bytes(16), 1)
+    codec = header[:-1].replace(po.zigzag_bytes(1), po.zigzag_bytes(2), 1) + po.zigzag_bytes(10) + b"avro.codec" + po.zigzag_bytes(7) + b"deflate" + po.zigzag_bytes(0)
+    with pytest.raises(ValueError, match="codec"):
+        pr.deserialize_ocf(codec + sync, 1)
