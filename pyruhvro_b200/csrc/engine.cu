@@ -793,7 +793,20 @@ rv_status decode_on_device(rv_schema* s, const uint8_t* d_data, const int64_t* d
         RV_CUDA(cudaEventRecord(ev[0], stream));
         if (use_jit) {
             void* args[] = {&p};
-            RV_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(jit.fused), dim3(unsigned(p.n_tiles)), dim3(kBlock), args, smem_bytes, stream));
+            const cudaError_t le = cudaLaunchKernel(reinterpret_cast<const void*>(jit.fused), dim3(unsigned(p.n_tiles)), dim3(kBlock), args, smem_bytes, stream);
+            if (le != cudaSuccess) {
+                // the driver rejected the specialised kernel (attributes, architecture): remember it for this
+                // (schema, device) and decode this call with the interpreter kernel instead — still on the GPU
+                (void)cudaGetLastError();
+                {
+                    std::lock_guard<std::mutex> g(s->mu);
+                    JitState& j = s->jit[device];
+                    j.ok = false;
+                    j.status = std::string("launch of the compiled walker was rejected: ") + cudaGetErrorString(le);
+                }
+                RV_CUDA(cudaStreamSynchronize(stream));
+                return decode_on_device(s, d_data, d_offsets, n, num_chunks, hints, stream, device, out, record_base);
+            }
         } else {
             launch_fused(p, smem_bytes, stream);
         }
