@@ -584,7 +584,7 @@ extern "C" int rv_last_encode_timings(float* out_ms, int cap) {
 // reach, size -> scan -> write, download of its chunks.  Returns a status; the message goes to *msg (worker threads have
 // their own thread-local error string).
 static rv_status encode_group(const AvroNode* top, const ArrowArray* batch, const ArrowSchema* batch_schema, int64_t g0, int64_t g1,
-                              int c0, int c1, int64_t chunk_rows, cudaStream_t stream, rv_encoded* res, std::mutex* res_mu, float* ms5,
+                              int c0, int c1, int64_t chunk_rows, cudaStream_t stream, rv_encoded* res, float* ms5,
                               std::string* msg) {
 #define GRP_CUDA(expr)                                                                                   \
     do {                                                                                                 \
@@ -752,10 +752,7 @@ static rv_status encode_group(const AvroNode* top, const ArrowArray* batch, cons
         const size_t bytes = off_bytes[size_t(j)] + size_t(c.data_bytes);
         void* h = rv_host_alloc(bytes + 64);
         if (!h) { *msg = "pinned allocation of an output chunk failed"; cudaStreamSynchronize(stream); return RV_ERR_CUDA; }
-        {
-            std::lock_guard<std::mutex> g(*res_mu);
-            res->keep.emplace_back(h, [](void* q) { rv_host_free(q); });
-        }
+        res->keep[size_t(c0 + j)] = std::shared_ptr<void>(h, [](void* q) { rv_host_free(q); });  // slot per chunk: rv_encoded_export(i) holds keep[i]
         c.host = h;
         GRP_CUDA(cudaMemcpyAsync(h, d_out[size_t(j)].p, bytes, cudaMemcpyDeviceToHost, stream));
     }
@@ -797,6 +794,7 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
     const int64_t chunk_rows = n / k;                 // slice_struct :19-30
     auto res = std::make_unique<rv_encoded>();
     res->chunks.resize(size_t(k));
+    res->keep.resize(size_t(k));
     for (int j = 0; j < k; ++j) res->chunks[size_t(j)].rows = (j == k - 1) ? n - chunk_rows * (k - 1) : chunk_rows;
 
     // Row groups of whole chunks, each on its own stream and host thread: the upload of group g+1 overlaps the kernels
@@ -807,14 +805,13 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
     std::vector<rv_status> status(size_t(groups), RV_OK);
     std::vector<std::string> message(static_cast<size_t>(groups));
     std::vector<std::array<float, 5>> times(static_cast<size_t>(groups), std::array<float, 5>{0, 0, 0, 0, 0});
-    std::mutex res_mu;
     auto run = [&](int g) {
         cudaSetDevice(device);
         const int c0 = int(int64_t(g) * k / groups), c1 = int(int64_t(g + 1) * k / groups);
         const int64_t g0 = int64_t(c0) * chunk_rows, g1 = (c1 == k) ? n : int64_t(c1) * chunk_rows;
         cudaStream_t stream = nullptr;
         if (groups > 1 && cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) { status[size_t(g)] = RV_ERR_CUDA; message[size_t(g)] = "stream creation failed"; return; }
-        status[size_t(g)] = encode_group(top, batch, batch_schema, g0, g1, c0, c1, chunk_rows, stream, res.get(), &res_mu, times[size_t(g)].data(), &message[size_t(g)]);
+        status[size_t(g)] = encode_group(top, batch, batch_schema, g0, g1, c0, c1, chunk_rows, stream, res.get(), times[size_t(g)].data(), &message[size_t(g)]);
         if (stream) cudaStreamDestroy(stream);
     };
     if (groups == 1) run(0);

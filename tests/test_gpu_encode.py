@@ -76,6 +76,32 @@ def test_large_batch_takes_the_staged_upload_and_round_trips():
         assert np.array_equal(lens, np.diff(off[lo:lo + b.num_rows + 1]))
 
 
+def test_row_groups_keep_each_chunk_alive_on_its_own():
+    """From 2^18 rows the chunks are encoded in concurrent row groups (encode.cu: rv_encode_host).  Every exported array
+    must own ITS chunk's memory: drop all but one array, churn the pinned cache with further calls, and the survivor
+    still holds its datums."""
+    import gc
+    import numpy as np
+    import workloads
+    n, k = 600_000, 8
+    sj, data, off = workloads.generate("kafka", n, seed=5)
+    batch = pr.decode_packed(data, off, n, sj, 1)[0]
+    rows = n // k
+    for keep in (0, 3, 7):
+        out = pr.serialize_record_batch(batch, sj, k)
+        assert [len(a) for a in out] == [rows] * (k - 1) + [n - rows * (k - 1)]
+        survivor = out[keep]
+        del out
+        gc.collect()
+        for _ in range(2):                                          # re-uses whatever the dropped arrays gave back
+            pr.serialize_record_batch(batch.slice(17, 300_000), sj, 5)
+        lo = keep * rows
+        o = np.frombuffer(survivor.buffers()[1], dtype=np.int32)[:len(survivor) + 1]
+        got = np.frombuffer(survivor.buffers()[2], dtype=np.uint8)[:o[-1]]
+        assert got.tobytes() == data[off[lo]:off[lo + len(survivor)]].tobytes()
+        assert np.array_equal(np.diff(o), np.diff(off[lo:lo + len(survivor) + 1]))
+
+
 def test_error_surface():
     recs = [bytes.fromhex(G.G2_HEX)]
     batch = pr.deserialize_array(recs, G.G2_SCHEMA)
