@@ -407,6 +407,40 @@ def c1_line(b):
             "fused_kernel_ms": float(dev["kernel_ms"][0]), "records_per_s_python": n / statistics.median(times)}
 
 
+def python_surface_line(b, n=1_000_000, k=8):
+    """(f)2: throughput through the Python surface at a size where it matters — the list walk + pinned gather of
+    `deserialize_array_threaded(list[bytes], ...)` (csrc/pymod.cpp) and the zero-copy `deserialize_arrow_array`
+    (a pyarrow BinaryArray of datums), next to the C-ABI call both of them end in."""
+    import pyarrow as pa
+    import pyruhvro
+    import workloads
+    pr = b.pr
+    sj, data, off = workloads.generate("kafka", n, seed=9)
+    recs = [data[off[i]:off[i + 1]].tobytes() for i in range(n)]
+    arr = pa.array(recs, type=pa.large_binary())
+
+    def med(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            out = fn()
+            ts.append(time.perf_counter() - t0)
+        assert sum(x.num_rows for x in out) == n
+        return statistics.median(ts)
+
+    t_list = med(lambda: pyruhvro.deserialize_array_threaded(recs, sj, k))
+    t_arrow = med(lambda: pr.deserialize_arrow_array(arr, sj, k))
+    t_abi = med(lambda: pr.decode_packed(data, off, n, sj, k))
+    return {"workload": "generate_avro.py schema, %d records, num_chunks = %d" % (n, k), "unit": UNIT,
+            "list_of_bytes": n / t_list, "list_of_bytes_ms": 1000.0 * t_list,
+            "arrow_binary_array": n / t_arrow, "arrow_binary_array_ms": 1000.0 * t_arrow,
+            "packed_numpy_c_abi": n / t_abi, "packed_numpy_c_abi_ms": 1000.0 * t_abi,
+            "note": "list_of_bytes = pyruhvro.deserialize_array_threaded (the reference's call); arrow_binary_array = deserialize_arrow_array "
+                    "(no list walk, no gather); packed = decode_packed -> rv_decode_host on pageable numpy buffers"}
+
+
 def config_line(b, workload, n, k, peak, peak_src, steps=10):
     w = b.load(workload, n, 42 if workload != "wide" else 43)
     dev = b.time_device(w, k, steps, 3)
@@ -578,7 +612,7 @@ def main():
         del w
         b.free_pinned()
         torch.cuda.empty_cache()
-        for key, fn in (("c1", lambda: c1_line(b)), ("c2", lambda: config_line(b, "flat", n, k, peak, peak_src)),
+        for key, fn in (("c1", lambda: c1_line(b)), ("python_surface", lambda: python_surface_line(b)), ("c2", lambda: config_line(b, "flat", n, k, peak, peak_src)),
                         ("c4", lambda: config_line(b, "wide", n, k, peak, peak_src))):
             try:
                 line[key] = fn()
