@@ -551,6 +551,65 @@ thread_local EventPool t_events;
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Upload of caller memory that is not page-locked (a Rust Vec, a numpy array): cudaMemcpyAsync would stage it inside the
+// driver on the calling thread at a fraction of the PCIe rate.  Each thread keeps two pinned pieces instead: the memcpy of
+// piece i+1 into one overlaps the DMA of piece i out of the other, and the chunk workers do this side by side.
+struct StageRing {
+    static constexpr size_t kPiece = size_t(8) << 20;
+    uint8_t* buf[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    int device = -1;
+    ~StageRing() { release(); }
+    void release() {
+        for (int i = 0; i < 2; ++i) {
+            if (buf[i]) cudaFreeHost(buf[i]);
+            if (done[i]) cudaEventDestroy(done[i]);
+            buf[i] = nullptr; done[i] = nullptr;
+        }
+        (void)cudaGetLastError();
+        device = -1;
+    }
+    bool ready(int dev) {
+        if (device == dev) return true;
+        release();
+        for (int i = 0; i < 2; ++i) {
+            if (cudaHostAlloc(reinterpret_cast<void**>(&buf[i]), kPiece, cudaHostAllocDefault) != cudaSuccess ||
+                cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) { release(); return false; }
+        }
+        device = dev;
+        return true;
+    }
+    // dst[0, bytes) <- src, in order on `stream`.  The pieces are free again when the stream has drained.
+    cudaError_t upload(uint8_t* dst, const uint8_t* src, size_t bytes, cudaStream_t stream) {
+        int slot = 0;
+        for (size_t o = 0; o < bytes; o += kPiece, slot ^= 1) {
+            const size_t len = std::min(kPiece, bytes - o);
+            cudaError_t e = cudaEventSynchronize(done[slot]);  // the DMA that last read this piece (no-op the first time)
+            if (e != cudaSuccess) return e;
+            std::memcpy(buf[slot], src + o, len);
+            e = cudaMemcpyAsync(dst + o, buf[slot], len, cudaMemcpyHostToDevice, stream);
+            if (e == cudaSuccess) e = cudaEventRecord(done[slot], stream);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+};
+thread_local StageRing t_stage;
+
+// true when `p` is ordinary pageable host memory (not pinned, registered, managed or device memory)
+bool is_pageable(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+// Host -> device on `stream`: through the calling thread's staging ring when the source is pageable and big enough to care.
+cudaError_t upload(uint8_t* dst, const uint8_t* src, size_t bytes, int device, cudaStream_t stream) {
+    if (bytes >= (size_t(1) << 20) && is_pageable(src) && t_stage.ready(device)) return t_stage.upload(dst, src, bytes, stream);
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+}
+
+
 // Error paths return cached device blocks (DevBuf) while work may still be queued on the stream: drain it first.
 struct SyncOnExit {
     cudaStream_t stream;
@@ -1108,8 +1167,8 @@ rv_status decode_host_range(rv_schema* s, const uint8_t* data, const int64_t* of
         cudaEventRecord(ev[4], stream);
         // The device copy keeps the caller's absolute offsets: the base pointer is biased so that
         // base + offsets[i] addresses record i (kept 16-byte aligned by the b0 & 15 shift).
-        cudaError_t e = cudaMemcpyAsync(static_cast<uint8_t*>(d_data.p) + (b0 & 15), data + b0, size_t(total), cudaMemcpyHostToDevice, stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_off.p, offsets + r0, size_t(n + 1) * 8, cudaMemcpyHostToDevice, stream);
+        cudaError_t e = upload(static_cast<uint8_t*>(d_data.p) + (b0 & 15), data + b0, size_t(total), device, stream);
+        if (e == cudaSuccess) e = upload(static_cast<uint8_t*>(d_off.p), reinterpret_cast<const uint8_t*>(offsets + r0), size_t(n + 1) * 8, device, stream);
         cudaEventRecord(ev[5], stream);
         if (e != cudaSuccess) { (void)cudaStreamSynchronize(stream); return fail(RV_ERR_CUDA, std::string("host->device copy: ") + cudaGetErrorString(e)); }
         base = static_cast<const uint8_t*>(d_data.p) + (b0 & 15) - b0;
@@ -1368,7 +1427,7 @@ extern "C" rv_status rv_decode_ocf_host(const uint8_t* file, int64_t len, int64_
     RV_CUDA(d_off.alloc(size_t(n + 1) * 8, stream));
     RV_CUDA(d_err.alloc(16, stream));
     SyncOnExit guard{stream};
-    RV_CUDA(cudaMemcpyAsync(d_file.p, file, size_t(len), cudaMemcpyHostToDevice, stream));
+    RV_CUDA(upload(static_cast<uint8_t*>(d_file.p), file, size_t(len), device, stream));
     if (n > 0) {
         DevicePlan dp;
         st = device_plan(s, device, &dp);

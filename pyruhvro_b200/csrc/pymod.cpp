@@ -50,15 +50,36 @@ bool pack_list(PyObject* list, Alloc alloc, Packed* out) {
     std::unique_ptr<const char*[]> ptrs(new const char*[static_cast<size_t>(n) + 1]);  // uninitialised on purpose
     int64_t* offsets = out->offsets;
     offsets[0] = 0;
-    for (Py_ssize_t i = 0; i < n; ++i) {
-        PyObject* item = PyList_GET_ITEM(list, i);
-        if (!PyBytes_Check(item)) {
-            PyErr_Format(PyExc_TypeError, "argument 'list': element %zd is '%s', expected 'bytes'", i, Py_TYPE(item)->tp_name);
-            return false;
+    const unsigned hw = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    // One read of every element's header: type check, payload pointer, size (left in offsets[i + 1]).  Long lists are
+    // walked by several threads — the calling thread holds the GIL throughout, so nothing they read can change.
+    auto walk = [list, offsets, p = ptrs.get()](Py_ssize_t a, Py_ssize_t b) -> Py_ssize_t {  // -> first non-bytes element, or b
+        for (Py_ssize_t i = a; i < b; ++i) {
+            PyObject* item = PyList_GET_ITEM(list, i);
+            if (!PyBytes_Check(item)) return i;
+            p[static_cast<size_t>(i)] = PyBytes_AS_STRING(item);
+            offsets[i + 1] = static_cast<int64_t>(PyBytes_GET_SIZE(item));
         }
-        ptrs[static_cast<size_t>(i)] = PyBytes_AS_STRING(item);
-        offsets[i + 1] = offsets[i] + static_cast<int64_t>(PyBytes_GET_SIZE(item));
+        return b;
+    };
+    Py_ssize_t bad = n;
+    if (n < (Py_ssize_t(1) << 16) || hw <= 1) {
+        bad = walk(0, n);
+    } else {
+        std::vector<Py_ssize_t> stop(hw, 0);
+        std::vector<std::thread> th;
+        for (unsigned w = 0; w < hw; ++w) {
+            const Py_ssize_t a = n / Py_ssize_t(hw) * Py_ssize_t(w), b = (w + 1 == hw) ? n : n / Py_ssize_t(hw) * Py_ssize_t(w + 1);
+            th.emplace_back([&stop, &walk, w, a, b] { const Py_ssize_t r = walk(a, b); stop[w] = r == b ? -1 : r; });
+        }
+        for (auto& t : th) t.join();
+        for (unsigned w = hw; w-- > 0;) if (stop[w] >= 0) bad = stop[w];   // the lowest failing index wins
     }
+    if (bad < n) {
+        PyErr_Format(PyExc_TypeError, "argument 'list': element %zd is '%s', expected 'bytes'", bad, Py_TYPE(PyList_GET_ITEM(list, bad))->tp_name);
+        return false;
+    }
+    for (Py_ssize_t i = 0; i < n; ++i) offsets[i + 1] += offsets[i];
     const int64_t total = offsets[n];
     out->total = total;
     out->data = static_cast<char*>(alloc(static_cast<size_t>(total) + 64));
@@ -66,7 +87,7 @@ bool pack_list(PyObject* list, Alloc alloc, Packed* out) {
         PyErr_SetString(PyExc_ValueError, "pinned host allocation failed (is a CUDA device present?)");
         return false;
     }
-    const unsigned workers = total > (int64_t(8) << 20) ? std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+    const unsigned workers = total > (int64_t(8) << 20) ? hw : 1u;
     char* dst = out->data;
     const char* const* src = ptrs.get();
     auto copy_range = [dst, src, offsets](Py_ssize_t a, Py_ssize_t b) {

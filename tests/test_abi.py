@@ -242,6 +242,13 @@ def test_list_packing_matches_binaryarray_from_vec():
     assert data == b"".join(skew)
     with pytest.raises(TypeError, match="element 1 is 'str', expected 'bytes'"):
         ext.pack([b"a", "b"])
+    long = [bytes([i & 255]) * (i % 7) for i in range(200_000)]       # >= 2^16 elements: the multi-threaded header walk
+    data, offs = ext.pack(long)
+    assert data == b"".join(long)
+    assert np.array_equal(np.frombuffer(offs, dtype=np.int64), np.concatenate([[0], np.cumsum([len(x) for x in long])]))
+    long[150_000], long[70_001], long[199_999] = None, 7, "s"          # several threads fail: the lowest index is reported
+    with pytest.raises(TypeError, match="element 70001 is 'int', expected 'bytes'"):
+        ext.pack(long)
     with pytest.raises(TypeError):
         ext.pack((b"a",))                                              # a list, like PyO3's Vec<Bound<PyBytes>> extraction
 
