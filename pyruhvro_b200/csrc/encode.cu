@@ -24,6 +24,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -811,13 +812,23 @@ rv_status rv_encode_host(const rv_schema* s, struct ArrowArray* batch, struct Ar
         const int64_t g0 = int64_t(c0) * chunk_rows, g1 = (c1 == k) ? n : int64_t(c1) * chunk_rows;
         cudaStream_t stream = nullptr;
         if (groups > 1 && cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) { status[size_t(g)] = RV_ERR_CUDA; message[size_t(g)] = "stream creation failed"; return; }
-        status[size_t(g)] = encode_group(top, batch, batch_schema, g0, g1, c0, c1, chunk_rows, stream, res.get(), times[size_t(g)].data(), &message[size_t(g)]);
+        try {
+            status[size_t(g)] = encode_group(top, batch, batch_schema, g0, g1, c0, c1, chunk_rows, stream, res.get(), times[size_t(g)].data(), &message[size_t(g)]);
+        } catch (const std::exception& e) {  // bad_alloc on a group's own thread must not terminate the process
+            cudaStreamSynchronize(stream);
+            (void)cudaGetLastError();
+            status[size_t(g)] = RV_ERR_INVALID;
+            message[size_t(g)] = e.what();
+        }
         if (stream) cudaStreamDestroy(stream);
     };
     if (groups == 1) run(0);
     else {
         std::vector<std::thread> pool;
-        for (int g = 1; g < groups; ++g) pool.emplace_back(run, g);
+        for (int g = 1; g < groups; ++g) {
+            try { pool.emplace_back(run, g); }
+            catch (const std::system_error&) { run(g); }   // no thread to be had: this group runs here
+        }
         run(0);
         for (auto& t : pool) t.join();
     }
