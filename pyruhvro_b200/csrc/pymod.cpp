@@ -31,6 +31,11 @@ namespace {
 // its cost.  The payload gather fans out over plain C++ threads (they touch no Python state).
 // `alloc(bytes)` returns the destination memory (pinned for the decode path).  Returns false with a Python
 // exception set.
+struct JoinAll {  // joins whatever was started, also when starting a later thread throws
+    std::vector<std::thread>& th;
+    ~JoinAll() { for (auto& t : th) if (t.joinable()) t.join(); }
+};
+
 struct Packed {
     char* data = nullptr;
     int64_t* offsets = nullptr;
@@ -68,6 +73,7 @@ bool pack_list(PyObject* list, Alloc alloc, Packed* out) {
     } else {
         std::vector<Py_ssize_t> stop(hw, 0);
         std::vector<std::thread> th;
+        JoinAll join_all{th};
         for (unsigned w = 0; w < hw; ++w) {
             const Py_ssize_t a = n / Py_ssize_t(hw) * Py_ssize_t(w), b = (w + 1 == hw) ? n : n / Py_ssize_t(hw) * Py_ssize_t(w + 1);
             th.emplace_back([&stop, &walk, w, a, b] { const Py_ssize_t r = walk(a, b); stop[w] = r == b ? -1 : r; });
@@ -98,6 +104,7 @@ bool pack_list(PyObject* list, Alloc alloc, Packed* out) {
     } else {
         // split by BYTES, not by element count, so skewed inputs still balance
         std::vector<std::thread> th;
+        JoinAll join_all{th};
         Py_ssize_t a = 0;
         for (unsigned w = 0; w < workers; ++w) {
             const int64_t want = total / int64_t(workers) * int64_t(w + 1);
