@@ -140,7 +140,7 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(k)
                 except Exception:
                     pass
-            time.sleep(0.004)
+            time.sleep(0.010)
 
     def stop(self):
         self._stop_evt.set()
