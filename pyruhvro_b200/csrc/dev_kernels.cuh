@@ -508,6 +508,7 @@ __device__ __forceinline__ void fused_body(const DecodeParams& p, const int tile
             st_state(p.tile_state + size_t(s) * p.n_tiles + t.lin, (t.local_tile == 0 ? kStPrefix : kStAgg) | tile_total);
         }
     }
+    __syncwarp();  // lane 0's ttot[s] stores above are read by the whole warp below
     // ---- chain the tile totals: exclusive prefix within the chunk
     for (int s = warp; s < p.n_streams; s += kWarps) {
         unsigned long long base = 0;
