@@ -352,8 +352,9 @@ class Bench:
 
 
 def traffic_of(workload, n):
-    """DRAM bytes per launch of the fused kernel from the committed ncu capture of this build (profiles/traffic.json,
-    written from an `ncu --set full` run; stale entries are ignored through the kernel-source hash)."""
+    """DRAM bytes per launch of the fused kernel from the committed ncu capture (profiles/traffic.json, written from an
+    `ncu --set full` run; the first entry for the workload and size is the current build's, older ones are kept marked
+    `superseded`)."""
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(tpath) as f:
