@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """One-off GPU fuzz campaign: many random schemas x random data, both walkers, buffer-exact vs the C oracle,
-plus encode round trips.  usage: fuzz_gpu.py [--warm] FIRST_SEED N_INTERP N_JIT"""
+plus encode round trips.  usage: fuzz_gpu.py [--warm] FIRST_SEED N_INTERP N_JIT
+    fuzz_gpu.py --wide FIRST_SEED N   random schemas over the WIDER subset (bytes, fixed, uuid, decimal, time-*, named
+                                      references) against the pure-Python oracle; every 16th case through a generated walker"""
 import os
 import random
 import sys
@@ -22,7 +24,32 @@ def warm(seed):
     return 1
 
 
+def main_wide(first, n_cases):
+    import pyruhvro_b200 as pr
+    from tests.parity import assert_matches_pyoracle_wide, gen_case_wide
+    bad = done = 0
+    for seed in range(first, first + n_cases):
+        rng = random.Random(seed * 31 + 7)
+        sj, recs, data, off = gen_case_wide(seed, n=rng.choice([1, 7, 255, 256, 257, 600, 1500]))
+        if not pr.Schema(sj).is_supported:
+            continue
+        k = rng.choice([1, 2, 8, 300])
+        pr.set_jit_enabled(1 if seed % 16 == 0 else 0)
+        try:
+            assert_matches_pyoracle_wide(pr.deserialize_array_threaded(recs, sj, k), sj, recs, k)
+            done += 1
+        except Exception as e:
+            bad += 1
+            print(f"FAIL seed={seed} k={k} n={len(recs)}: {type(e).__name__}: {str(e)[:300]}\n  schema={sj[:400]}", flush=True)
+    pr.set_jit_enabled(-1)
+    print(f"wide fuzz done: first={first} cases={done} failures={bad}", flush=True)
+    sys.exit(1 if bad else 0)
+
+
 def main():
+    if "--wide" in sys.argv:
+        a = [x for x in sys.argv[1:] if x != "--wide"]
+        return main_wide(int(a[0]), int(a[1]))
     args = [a for a in sys.argv[1:] if a != "--warm"]
     first, n_interp, n_jit = int(args[0]), int(args[1]), int(args[2])
     if "--warm" in sys.argv:
