@@ -79,8 +79,10 @@ rv_status rv_schema_export_arrow(const rv_schema* s, struct ArrowSchema* out);
  * partitioned like build_slices (:57-68): chunk = n / k, the last chunk takes the remainder;
  * one RecordBatch per chunk, in order.  n = 0 yields one empty batch.
  *
- * Host variant: `data`/`offsets` are host memory (pinned memory from rv_host_alloc gives full
- * PCIe bandwidth); the batches' buffers land in library-owned pinned host memory. */
+ * Host variant: `data`/`offsets` are host memory.  Page-locked memory (rv_host_alloc, cudaHostAlloc,
+ * cudaHostRegister) is copied from directly; ordinary pageable memory (a Rust Vec, a numpy array) is
+ * recognised and uploaded through the library's pinned staging pieces, overlapped with the transfer.
+ * The batches' buffers land in library-owned pinned host memory. */
 rv_status rv_decode_host(const rv_schema* s, const uint8_t* data, const int64_t* offsets, int64_t n,
                          int64_t num_chunks, rv_result** out);
 
