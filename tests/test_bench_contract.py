@@ -37,3 +37,16 @@ def test_usable_cores_respects_affinity_and_quota():
     assert 1 <= n <= aff
     if quota is not None:
         assert n <= max(1, int(quota + 0.999))
+
+
+def test_roofline_traffic_comes_from_a_committed_capture():
+    """`roofline.traffic` of the bench line is the DRAM byte count of a committed ncu capture of the fused kernel for the
+    bench's own workload and size (the first, current, entry of profiles/traffic.json) and names that capture."""
+    sys.path.insert(0, ROOT)
+    import bench
+    traffic, capture = bench.traffic_of("kafka", 10_000_000)
+    assert isinstance(traffic, int) and traffic > 0
+    algorithmic = 1_170_821_397 + 80_000_008 + 1_670_247_592          # SURVEY 8(d): input + offsets + Arrow buffers
+    assert 0.9 * algorithmic < traffic < 1.2 * algorithmic             # the fused pass reads the input once
+    assert capture and os.path.exists(os.path.join(ROOT, capture.split(" ")[0]))
+    assert bench.traffic_of("kafka", 123) == (None, None)              # no capture for other sizes: reported as null
