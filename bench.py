@@ -367,6 +367,31 @@ def traffic_of(workload, n):
     return None, None
 
 
+def bind_to_gpu_node(torch, local_rank):
+    """Runs this rank's threads on the CPUs of its GPU's NUMA node (what `numactl --cpunodebind` would do per rank): the
+    calling thread's driver calls, the template / read-back copies and the library's workers stay on the GPU's socket.
+    Returns the node, or None when it cannot be determined (then nothing changes)."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def parity_check(b, w, k):
     """Outside every timed region: the exact arena the bench times, decoded through the host C ABI and through the
     device-resident path, compared buffer-for-buffer with the C oracle (the checker; never the thing measured)."""
@@ -555,6 +580,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the decode path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_node(torch, local_rank) if world > 1 else None   # one rank per GPU: each on its GPU's socket
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     b = Bench(args, rank, local_rank, world)
@@ -569,12 +595,15 @@ def main():
     n, k = args.records, args.num_chunks
     w = b.load(args.workload, n, args.seed, r0=rank * n)
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-    sampler = ClockSampler(int(vis.split(",")[local_rank]) if vis else local_rank)
-    sampler.start()
+    # the line carries rank 0's clocks; the other ranks do not poll NVML (eight pollers contend on the driver for nothing)
+    sampler = ClockSampler(int(vis.split(",")[local_rank]) if vis else local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
 
     dev_res = b.time_device(w, k, steps, warmup, sampler)
     host_res = b.time_host(w, k, steps, warmup, sampler)
-    sampler.stop()
+    if sampler:
+        sampler.stop()
     value = world * n / (dev_res["ms_per_step"] * 1e-3)
     e2e_value = world * n / (host_res["ms_per_step"] * 1e-3)
 
@@ -598,8 +627,10 @@ def main():
                 "path": "rv_decode_host: pinned host Avro in -> pinned host Arrow out, chunks pipelined on persistent NUMA-bound workers"},
         "gpu_launches": dev_res["launches"],
         "roofline": rl,
-        "clocks": sampler.summary(),
+        "clocks": sampler.summary() if sampler else None,
     }
+    if world > 1:
+        line["rank_binding"] = {"rank0_numa_node": numa_node, "how": "each rank's threads run on the CPUs of its GPU's NUMA node (bench.py: bind_to_gpu_node)"}
     if world == 1 and not args.no_extras:
         try:
             line["parity_checked"] = parity_check(b, w, k)
