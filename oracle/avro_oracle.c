@@ -527,7 +527,7 @@ static void decode_value(dec *d, cursor *c) {
     case D_LIST: case D_MAP: /* :703-719, :745-762 */
         for (;;) {
             int64_t n = read_zigzag_long(c); if (c->err) return; /* read_block_count :689-700 */
-            if (n < 0) { (void)read_zigzag_long(c); if (c->err) return; n = -n; }
+            if (n < 0) { (void)read_zigzag_long(c); if (c->err) return; n = (int64_t)(0 - (uint64_t)n); } /* `-n` wraps in the release build: i64::MIN stays negative and `0..n` is empty */
             if (n == 0) break;
             for (int64_t i = 0; i < n; i++) {
                 if (d->k == D_MAP) {

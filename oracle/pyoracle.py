@@ -635,9 +635,11 @@ def _decode(d: _Dec, c: _Cur):
             if n < 0:
                 c.zigzag()
                 n = -n
+                if n >= 1 << 63:   # `-n` wraps in the release build: i64::MIN stays negative and `0..n` is an empty range
+                    n -= 1 << 64
             if n == 0:
                 break
-            for _ in range(n):
+            for _ in range(max(n, 0)):
                 if k == "map":
                     key = d.children[0]
                     key.values += c.string()

@@ -704,13 +704,16 @@ RV_HD int rd_block(C& c, int64_t& rem, uint32_t& total, bool zero_items) {
 }
 
 // After every item of a list / map in COUNT mode: true = leave the loop.  PRECISE: the first error parked the
-// cursor.  FAST: the deferred end-of-buffer check, which also bounds a garbage block count.
+// cursor.  FAST: the deferred end-of-buffer check — and ANY "not plain" flag: the lane's fast result is thrown away
+// then, and this is what bounds a garbage block count.  (The end-of-buffer test alone does not: an item whose last
+// node reads nothing — an unselected union variant, a nested list that just stopped — leaves the cursor parked AT
+// the end by eof_check / the inner item_stop, and a forged count of 2^63 would be walked in full.)
 template <int MODE, class C>
 RV_HD bool item_stop(C& c) {
     if (MODE != WM_COUNT) return false;
     if (C::kShared) {
         if (c.pos > c.end) { c.err |= E_EOF; c.pos = c.end; return true; }
-        return false;
+        return c.err != 0;
     }
     return c.err != 0;
 }
