@@ -919,7 +919,7 @@ class _OrcArray(ctypes.Structure):
 
 _DKIND = ["int32", "int64", "float32", "float64", "bool", "utf8", "int32", "int64", "int64", "utf8",
           "null", "struct", "union", "list", "map"]
-ERR_NAMES = {0: "ok", 1: "eof", 2: "varint", 3: "bool", 4: "neg_len", 5: "branch", 6: "enum", 7: "schema", 8: "overflow"}
+ERR_NAMES = {0: "ok", 1: "eof", 2: "varint", 3: "bool", 4: "neg_len", 5: "branch", 6: "enum", 7: "schema", 8: "overflow", 11: "value", 12: "frame"}
 
 
 def build_oracle(force: bool = False) -> str:

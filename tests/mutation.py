@@ -82,3 +82,38 @@ def check(coracle, decode, error_of, sj, recs, k):
     assert want is None, f"decoder accepted a batch the reference rejects with {want}"
     assert_matches_oracle(coracle, got, sj, data, off, len(recs), k, full_validate=False)   # (damaged strings need not be UTF-8)
     return "decoded"
+
+
+# ---- the wider subset: the checker is the pure-Python oracle (the reference cannot decode these schemas at all) ----------
+def damaged_case_wide(seed: int):
+    from tests.parity import gen_case_wide
+    rng = random.Random(seed * 977 + 5)
+    sj, recs, _, _ = gen_case_wide(seed, n=rng.choice([3, 40, 257]))
+    return sj, damage(rng, recs), rng.choice([1, 2, 3])
+
+
+def expected_wide(sj, recs):
+    s = po.parse_schema(sj, wide=True)
+    for i, r in enumerate(recs):      # py_decode raises without an index: first failing record, one at a time
+        try:
+            po.py_decode(s, [r])
+        except po.DecodeError as e:
+            return (e.code, i)
+    return None
+
+
+def check_wide(decode, error_of, sj, recs, k):
+    from tests.parity import assert_matches_pyoracle_wide
+    data, off = po.pack_records(recs)
+    want = expected_wide(sj, recs)
+    try:
+        got = decode(sj, data, off, len(recs), k)
+    except Exception as e:  # noqa: BLE001
+        g = error_of(e)
+        if g is None:
+            raise
+        assert g == want, f"decoder reports {g}, the oracle {want}"
+        return "error"
+    assert want is None, f"decoder accepted a batch the oracle rejects with {want}"
+    assert_matches_pyoracle_wide(got, sj, recs, k, full_validate=False)
+    return "decoded"

@@ -53,3 +53,10 @@ def test_damaged_batches_interpreter(coracle, seed):
 def test_damaged_batches_generated_walkers(coracle, seed):
     sj, recs, k = M.damaged_case(seed, schema_seed=100 + seed % 12)   # the schemas test_emu_parity.py already compiles
     M.check(coracle, _emu("gen"), _emu_error, sj, recs, k)
+
+
+@pytest.mark.parametrize("seed", range(950000, 950100))
+def test_damaged_batches_wider_subset(seed):
+    """bytes / fixed / uuid / decimal / time-* / named references: value errors (RV_ERR_VALUE) included."""
+    sj, recs, k = M.damaged_case_wide(seed)
+    M.check_wide(_emu("interp"), _emu_error, sj, recs, k)
