@@ -245,7 +245,12 @@ bool supported_inner(const AvroNode& n, std::string* why) {
     switch (n.k) {
         case AK::Int: case AK::Long: case AK::Float: case AK::Double: case AK::Bool: case AK::String: case AK::Null:
         case AK::Date: case AK::TsMillis: case AK::TsMicros: case AK::Enum:
-        case AK::Bytes: case AK::Fixed: case AK::DecimalBytes: case AK::DecimalFixed: case AK::Uuid: case AK::TimeMillis: case AK::TimeMicros:
+        case AK::Bytes: case AK::DecimalBytes: case AK::Uuid: case AK::TimeMillis: case AK::TimeMicros:
+            return true;
+        case AK::Fixed: case AK::DecimalFixed:
+            // a fixed of size 0 spends no wire bytes: an 8-byte list header could then announce 2^31 items, each of them
+            // walked — unbounded work for bounded input.  (The reference's fast path takes no fixed at all.)
+            if (n.size == 0) { if (why) *why = "fixed of size 0"; return false; }
             return true;
         case AK::Record:
             for (auto& f : n.fields)

@@ -92,12 +92,16 @@ def test_schema_translation_and_gate():
     for seed in range(120):
         sj = po.random_schema_json(random.Random(seed), wide=True)
         assert pr.Schema(sj).arrow_schema.equals(expected_schema_wide(sj), check_metadata=True), sj
-    # still outside: recursion, 256-bit decimals, duration, local timestamps
+    # still outside: recursion, 256-bit decimals, duration, local timestamps, and a fixed of size 0 (no wire bytes per value:
+    # a list header could announce 2^31 of them)
     for bad in ['{"type":"record","name":"R","fields":[{"name":"next","type":["null","R"]}]}',
+                '{"type":"record","name":"R","fields":[{"name":"a","type":{"type":"array","items":{"type":"fixed","name":"F","size":0}}}]}',
+                '{"type":"record","name":"R","fields":[{"name":"d","type":{"type":"fixed","name":"D","size":0,"logicalType":"decimal","precision":1}}]}',
                 '{"type":"record","name":"R","fields":[{"name":"d","type":{"type":"bytes","logicalType":"decimal","precision":39,"scale":0}}]}',
                 '{"type":"record","name":"R","fields":[{"name":"d","type":{"type":"fixed","name":"D","size":12,"logicalType":"duration"}}]}',
                 '{"type":"record","name":"R","fields":[{"name":"t","type":{"type":"long","logicalType":"local-timestamp-millis"}}]}']:
         assert not pr.Schema(bad).is_supported, bad
+        assert not po.is_supported(po.parse_schema(bad, wide=True)), bad
 
 
 @pytest.mark.parametrize("walker", ["interp", "gen"])
