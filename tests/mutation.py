@@ -84,6 +84,62 @@ def check(coracle, decode, error_of, sj, recs, k):
     return "decoded"
 
 
+# ---- forged varints: structured damage (a second generator; `damage` above and its seeds stay as they are) --------------
+# Values a length / count / index / branch reader has an edge at, canonical and not.
+FORGED_INTS = [0, 1, -1, 2, 63, 64, -64, -65, 127, 128, 255, 256, 257, 300, 8191, 8192, 2**20, 2**30, -2**30, 2**31 - 2, 2**31 - 1, 2**31,
+               -2**31, -2**31 - 1, 2**32 - 1, 2**32, 2**42, 2**56, 2**62, -2**62, 2**63 - 1, -2**63 + 1, -2**63]
+
+
+def _leb128(u: int) -> bytes:
+    out = bytearray()
+    while True:
+        b = u & 0x7F
+        u >>= 7
+        if u:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def forged_varint(rng: random.Random) -> bytes:
+    r = rng.random()
+    if r < 0.6:
+        return po.zigzag_bytes(rng.choice(FORGED_INTS))
+    if r < 0.75:   # not canonical: the same value padded with continuation bytes
+        b = bytearray(po.zigzag_bytes(rng.choice(FORGED_INTS[:12])))
+        b[-1] |= 0x80
+        return bytes(b) + b"\x80" * rng.randrange(0, 8) + b"\x00"
+    if r < 0.85:   # raw 64-bit patterns (the top bit of the tenth byte, all ones)
+        return _leb128(rng.choice([2**64 - 1, 2**63, 2**64 - 2, 2**35, 2**63 - 1]))
+    if r < 0.93:   # too long
+        return b"\xff" * rng.randrange(9, 12) + bytes([rng.randrange(256)])
+    return po.zigzag_bytes(rng.randrange(-2**63, 2**63))
+
+
+def forge_varints(rng: random.Random, recs):
+    """One to three forged varints per batch, each either spliced in or written over the varint that starts at a random byte."""
+    recs = [bytearray(r) for r in recs]
+    for _ in range(rng.choice([1, 1, 2, 3])):
+        r = recs[rng.randrange(len(recs))]
+        v = forged_varint(rng)
+        j = rng.randrange(len(r) + 1)
+        if rng.random() < 0.5 and j < len(r):
+            e = j
+            while e < len(r) and r[e] & 0x80 and e - j < 10:
+                e += 1
+            r[j:e + 1] = v
+        else:
+            r[j:j] = v
+    return [bytes(r) for r in recs]
+
+
+def forged_case(seed: int, schema_seed=None):
+    rng = random.Random(seed * 7919 + 11)
+    sj, recs, _, _ = gen_case(seed if schema_seed is None else schema_seed, n=rng.choice([3, 40, 257, 300]))
+    return sj, forge_varints(rng, recs), rng.choice([1, 2, 3, 8])
+
+
 # ---- the wider subset: the checker is the pure-Python oracle (the reference cannot decode these schemas at all) ----------
 def damaged_case_wide(seed: int):
     from tests.parity import gen_case_wide

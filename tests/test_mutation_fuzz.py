@@ -55,6 +55,19 @@ def test_damaged_batches_generated_walkers(coracle, seed):
     M.check(coracle, _emu("gen"), _emu_error, sj, recs, k)
 
 
+@pytest.mark.parametrize("seed", range(960000, 960200))
+def test_forged_varints_interpreter(coracle, seed):
+    """Structured damage: edge-value, padded, over-long and raw 64-bit varints spliced in or written over existing ones."""
+    sj, recs, k = M.forged_case(seed)
+    M.check(coracle, _emu("interp"), _emu_error, sj, recs, k)
+
+
+@pytest.mark.parametrize("seed", range(970000, 970060))
+def test_forged_varints_generated_walkers(coracle, seed):
+    sj, recs, k = M.forged_case(seed, schema_seed=100 + seed % 12)
+    M.check(coracle, _emu("gen"), _emu_error, sj, recs, k)
+
+
 @pytest.mark.parametrize("seed", range(950000, 950100))
 def test_damaged_batches_wider_subset(seed):
     """bytes / fixed / uuid / decimal / time-* / named references: value errors (RV_ERR_VALUE) included."""

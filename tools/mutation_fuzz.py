@@ -3,7 +3,9 @@
 says whether the batch still decodes (then every buffer must match) or which record fails first with which category (then
 the implementation under test must say the same).
 
-    python tools/mutation_fuzz.py FIRST_SEED N [emu-interp | emu-gen | gpu-interp | gpu-jit]
+    python tools/mutation_fuzz.py FIRST_SEED N [emu-interp | emu-gen | gpu-interp | gpu-jit] [--forge]
+
+--forge: structured damage instead (tests/mutation.forge_varints: edge-value / padded / over-long varints spliced in).
 
 emu-*: the host emulation of the product's readers (no GPU); gpu-*: the CUDA path through rv_decode_host.  emu-gen and
 gpu-jit draw their schemas from 80 seeds (one compilation each)."""
@@ -16,8 +18,10 @@ sys.path.insert(0, ROOT)
 
 
 def main():
-    first, count = int(sys.argv[1]), int(sys.argv[2])
-    mode = sys.argv[3] if len(sys.argv) > 3 else "emu-interp"
+    forge = "--forge" in sys.argv
+    argv = [a for a in sys.argv if a != "--forge"]
+    first, count = int(argv[1]), int(argv[2])
+    mode = argv[3] if len(argv) > 3 else "emu-interp"
     from oracle import pyoracle as po
     from tests import mutation as M
     co = po.COracle()
@@ -37,7 +41,7 @@ def main():
     bad = 0
     t0 = time.time()
     for seed in range(first, first + count):
-        sj, recs, k = M.damaged_case(seed, schema_seed=7000 + seed % 80 if few else None)
+        sj, recs, k = (M.forged_case if forge else M.damaged_case)(seed, schema_seed=7000 + seed % 80 if few else None)
         if not supported(sj):
             continue
         try:
@@ -45,7 +49,7 @@ def main():
         except AssertionError as e:
             bad += 1
             print(f"FAIL seed={seed} k={k}: {str(e)[:300]}", flush=True)
-    print(f"mutation fuzz ({mode}): decoded-equal {seen['decoded']}, same-error {seen['error']}, failures {bad}, {int(time.time() - t0)} s")
+    print(f"mutation fuzz ({mode}{', forged varints' if forge else ''}): decoded-equal {seen['decoded']}, same-error {seen['error']}, failures {bad}, {int(time.time() - t0)} s")
     sys.exit(1 if bad else 0)
 
 
