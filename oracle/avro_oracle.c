@@ -152,7 +152,7 @@ static jval *jparse(jparser *P) {
 }
 static jval *jget(const jval *o, const char *key) {
     if (!o || o->k != J_OBJ) return NULL;
-    for (int i = 0; i < o->n; i++) if (!strcmp(o->keys[i], key)) return o->items[i];
+    for (int i = o->n - 1; i >= 0; i--) if (!strcmp(o->keys[i], key)) return o->items[i]; /* a repeated key: the last one wins (serde_json Map::insert) */
     return NULL;
 }
 

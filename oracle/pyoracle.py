@@ -147,11 +147,12 @@ def _parse(j: Any, ns: Optional[str], wide: bool = False, names: Optional[_Names
         full, fns = _name(j, ns)
         size = int(j["size"])
         lt = j.get("logicalType")
+        f = None
         if lt == "decimal":
             f = _decimal("decimal-fixed", j, size)
         elif lt == "duration":
             f = AvroSchema("unsupported")
-        else:
+        if f is None:
             f = AvroSchema("fixed", size=size)
         f.fullname, f.doc, f.aliases = full, j.get("doc"), _fix_aliases(j.get("aliases"), fns)
         if f.kind != "unsupported":
@@ -170,10 +171,16 @@ def _is_named_ref(t: str, ns: Optional[str], names: _Names) -> bool:
     return q in names.done or q in names.open or t in names.done or t in names.open
 
 
-def _decimal(kind: str, obj: dict, size: int) -> AvroSchema:
-    precision, scale = int(obj.get("precision", -1)), int(obj.get("scale", 0))
+def _decimal(kind: str, obj: dict, size: int) -> Optional[AvroSchema]:
+    """None: invalid precision / scale.  apache-avro 0.21 then ignores the logical type with a warning ("Ignoring invalid
+    decimal logical type") and the schema is the underlying bytes / fixed; precision and scale must be JSON numbers that are
+    non-negative integers (parse_json_integer_for_decimal), only "scale" may be absent (0)."""
+    def meta(key, absent):
+        v = obj.get(key, absent) if obj else absent
+        return v if isinstance(v, int) and not isinstance(v, bool) and 0 <= v < 10**9 else -1
+    precision, scale = meta("precision", -1), meta("scale", 0)
     if precision < 1 or scale < 0 or scale > precision:
-        raise ValueError("decimal needs 1 <= precision and 0 <= scale <= precision")
+        return None
     if precision > 38 or (kind == "decimal-fixed" and size > 16):
         return AvroSchema("unsupported")
     return AvroSchema(kind, size=size, precision=precision, scale=scale)
@@ -206,7 +213,7 @@ def _prim(t: str, obj: Optional[dict], wide: bool = False, ns: Optional[str] = N
     if not wide:
         return AvroSchema("unsupported")  # bytes, fixed, named Ref (fast_decode.rs:59)
     if t == "bytes":
-        return _decimal("decimal-bytes", obj, 0) if lt == "decimal" else AvroSchema("bytes")
+        return (_decimal("decimal-bytes", obj, 0) if lt == "decimal" else None) or AvroSchema("bytes")
     if names is not None:
         for cand in ((f"{ns}.{t}" if "." not in t and ns else t), t):
             if cand in names.open:

@@ -119,7 +119,13 @@ class JsonReader {
                 ws();
                 if (p_ >= end_ || *p_ != ':') fail("expected ':'");
                 ++p_;
-                v.obj.emplace_back(std::move(k), value(depth + 1));
+                Json item = value(depth + 1);
+                // a repeated key replaces the earlier value (serde_json's Map::insert, which apache_avro's
+                // Schema::parse_str reads the document into: the last occurrence wins)
+                bool replaced = false;
+                for (auto& kv : v.obj)
+                    if (kv.first == k) { kv.second = std::move(item); replaced = true; break; }
+                if (!replaced) v.obj.emplace_back(std::move(k), std::move(item));
                 ws();
                 if (p_ < end_ && *p_ == ',') { ++p_; continue; }
                 if (p_ < end_ && *p_ == '}') { ++p_; return v; }

@@ -47,6 +47,18 @@ struct Names {
     std::set<std::string> open;
 };
 
+// [A-Za-z_][A-Za-z0-9_]* — what apache-avro's validators ask of a type's short name, a record field's name and an enum
+// symbol (validate_schema_name / validate_record_field_name / validate_enum_symbol_name: the specification's names).
+bool is_identifier(const std::string& s) {
+    if (s.empty()) return false;
+    for (size_t i = 0; i < s.size(); ++i) {
+        const unsigned char c = static_cast<unsigned char>(s[i]);
+        const bool alpha = (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_';
+        if (!(alpha || (i > 0 && c >= '0' && c <= '9'))) return false;
+    }
+    return true;
+}
+
 // Name resolution as apache-avro does it: a dotted name carries its own namespace,
 // otherwise the "namespace" attribute, otherwise the enclosing namespace.
 void resolve_name(const Json& j, const std::string& enclosing_ns, std::string* fullname, std::string* ns) {
@@ -54,6 +66,16 @@ void resolve_name(const Json& j, const std::string& enclosing_ns, std::string* f
     if (!nm || !nm->is_string() || nm->str.empty()) bad("named type without a \"name\"");
     const std::string& name = nm->str;
     size_t dot = name.rfind('.');
+    // Name::new -> validate_schema_name: the part behind the last dot is an identifier; the namespace part in front of it
+    // is made of identifier characters and dots and does not start with a digit.  (Only what every published form of
+    // that pattern rejects is rejected here.)
+    if (!is_identifier(dot == std::string::npos ? name : name.substr(dot + 1))) bad("invalid name \"" + name + "\" (must match [A-Za-z_][A-Za-z0-9_]*, optionally behind a dotted namespace)");
+    if (dot != std::string::npos)
+        for (size_t i = 0; i < dot; ++i) {
+            const unsigned char c = static_cast<unsigned char>(name[i]);
+            const bool ok = (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_' || c == '.' || (i > 0 && c >= '0' && c <= '9');
+            if (!ok) bad("invalid namespace in the name \"" + name + "\"");
+        }
     std::string shortname;
     if (dot != std::string::npos) {
         *ns = name.substr(0, dot);
@@ -69,11 +91,16 @@ void resolve_name(const Json& j, const std::string& enclosing_ns, std::string* f
 void read_doc_aliases(const Json& j, const std::string& ns, AvroNode* n) {
     if (const Json* d = j.find("doc"); d && d->is_string()) { n->has_doc = true; n->doc = d->str; }
     if (const Json* a = j.find("aliases"); a && a->kind == Json::Array) {
-        n->has_aliases = true;
-        for (auto& al : a->arr) {
-            if (!al.is_string()) bad("alias must be a string");
-            if (al.str.find('.') == std::string::npos && !ns.empty()) n->aliases.push_back(ns + "." + al.str);
-            else n->aliases.push_back(al.str);
+        // (an "aliases" array with anything but strings in it is no aliases at all: apache-avro collects them into an
+        // Option and drops the lot, it does not fail)
+        bool all_strings = true;
+        for (auto& al : a->arr) all_strings = all_strings && al.is_string();
+        if (all_strings) {
+            n->has_aliases = true;
+            for (auto& al : a->arr) {
+                if (al.str.find('.') == std::string::npos && !ns.empty()) n->aliases.push_back(ns + "." + al.str);
+                else n->aliases.push_back(al.str);
+            }
         }
     }
 }
@@ -84,10 +111,24 @@ int json_int(const Json* j, int dflt) {
     return dflt;
 }
 
+// "precision" / "scale" of a decimal as apache-avro reads them (parse_json_integer_for_decimal): a JSON number that is a
+// non-negative integer ("4", not "4.0", "-4" or "4e0").  -1: anything else.
+long long decimal_meta(const Json* j) {
+    if (!j || j->kind != Json::Number || j->str.empty() || j->str.size() > 9) return -1;
+    for (char c : j->str)
+        if (c < '0' || c > '9') return -1;
+    return std::strtoll(j->str.c_str(), nullptr, 10);
+}
+
+// nullptr: the decimal annotation is invalid.  apache-avro then IGNORES the logical type ("Ignoring invalid decimal logical
+// type", a warning) and the schema is the underlying bytes / fixed — it does not fail, and it never guesses a scale.
 std::unique_ptr<AvroNode> decimal_of(AK k, const Json* obj, int size) {
-    const int precision = json_int(obj ? obj->find("precision") : nullptr, -1);
-    const int scale = json_int(obj ? obj->find("scale") : nullptr, 0);
-    if (precision < 1 || scale < 0 || scale > precision) bad("decimal needs 1 <= precision and 0 <= scale <= precision");
+    const Json* pj = obj ? obj->find("precision") : nullptr;
+    const Json* sj = obj ? obj->find("scale") : nullptr;
+    const long long p = decimal_meta(pj);
+    const long long sc = sj ? decimal_meta(sj) : 0;   // (only "scale" may be absent: 0)
+    if (p < 1 || sc < 0 || sc > p) return nullptr;
+    const int precision = int(p), scale = int(sc);
     if (precision > 38) return unsupported("decimal with precision above 38 (Decimal128)");
     if (k == AK::DecimalFixed && size > 16) return unsupported("decimal on a fixed wider than 16 bytes");
     auto n = mk(k);
@@ -121,7 +162,8 @@ std::unique_ptr<AvroNode> primitive(const std::string& t, const Json* obj, const
         return mk(AK::String);
     }
     if (t == "bytes") {
-        if (lt == "decimal") return decimal_of(AK::DecimalBytes, obj, 0);
+        if (lt == "decimal")
+            if (auto d = decimal_of(AK::DecimalBytes, obj, 0)) return d;
         return mk(AK::Bytes);
     }
     // a reference to a named type defined earlier in the document (Schema::Ref)
@@ -184,6 +226,9 @@ std::unique_ptr<AvroNode> parse_node(const Json& j, const std::string& ns, int d
             const Json* ft = fj.find("type");
             if (!fn || !fn->is_string() || !ft) bad("record field needs \"name\" and \"type\"");
             f.name = fn->str;
+            if (!is_identifier(f.name)) bad("invalid record field name \"" + f.name + "\" (must match [A-Za-z_][A-Za-z0-9_]*)");   // validate_record_field_name
+            for (const AvroField& earlier : r->fields)
+                if (earlier.name == f.name) bad("duplicate record field name \"" + f.name + "\"");   // Error::FieldNameDuplicate
             // apache-avro 0.21 parses a record field by handing the FIELD object to its complex-type parser
             // (RecordField::parse -> Parser::parse_complex(field, ..)), so when "type" is a bare string the
             // attributes of that type are read from the field object itself: {"name":"xs","type":"array","items":..}
@@ -210,6 +255,9 @@ std::unique_ptr<AvroNode> parse_node(const Json& j, const std::string& ns, int d
         if (!sy || sy->kind != Json::Array) bad("enum without a \"symbols\" array");
         for (auto& s : sy->arr) {
             if (!s.is_string()) bad("enum symbols must be strings");
+            if (!is_identifier(s.str)) bad("invalid enum symbol \"" + s.str + "\" (must match [A-Za-z_][A-Za-z0-9_]*)");   // validate_enum_symbol_name
+            for (const std::string& earlier : e->symbols)
+                if (earlier == s.str) bad("duplicate enum symbol \"" + s.str + "\"");   // Error::EnumSymbolDuplicate
             e->symbols.push_back(s.str);
         }
         names.done[e->fullname] = e.get();
@@ -225,7 +273,7 @@ std::unique_ptr<AvroNode> parse_node(const Json& j, const std::string& ns, int d
         std::unique_ptr<AvroNode> f;
         if (lt == "decimal") f = decimal_of(AK::DecimalFixed, &j, size);
         else if (lt == "duration") f = unsupported("duration");
-        else { f = mk(AK::Fixed); f->size = size; }
+        if (!f) { f = mk(AK::Fixed); f->size = size; }
         f->fullname = fullname;
         read_doc_aliases(j, fns, f.get());
         if (f->k != AK::Unsupported) names.done[fullname] = f.get();

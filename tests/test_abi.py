@@ -129,6 +129,55 @@ def test_schema_parse_errors_are_value_errors():
             pr.Schema(bad)
 
 
+def _rec(field_json: str, name: str = "T") -> str:
+    return '{"type":"record","name":"%s","fields":[%s]}' % (name, field_json)
+
+
+@pytest.mark.parametrize("bad", [
+    _rec('{"name":" x","type":"int"}'), _rec('{"name":"9x","type":"int"}'), _rec('{"name":"a-b","type":"int"}'), _rec('{"name":"","type":"int"}'),
+    _rec('{"name":"a","type":"int"},{"name":"a","type":"long"}'),                       # Error::FieldNameDuplicate
+    _rec('{"name":"a","type":"int"}', name="x y"), _rec('{"name":"a","type":"int"}', name="R."), _rec('{"name":"a","type":"int"}', name="9ns.R"),
+    _rec('{"name":"e","type":{"type":"enum","name":"E","symbols":["A","A"]}}'),       # Error::EnumSymbolDuplicate
+    _rec('{"name":"e","type":{"type":"enum","name":"E","symbols":["1A"]}}'), _rec('{"name":"e","type":{"type":"enum","name":"E","symbols":["A-B"]}}'),
+    _rec('{"name":"e","type":{"type":"enum","name":"E","symbols":[""]}}'),
+])
+def test_names_and_symbols_are_validated_like_apache_avro(bad):
+    """Schema::parse_str (apache-avro 0.21, the reference's `parse_schema`, deserialize.rs:18-20) validates type names,
+    record field names and enum symbols against the specification's pattern and rejects repeated field names and repeated
+    enum symbols; the reference then raises ValueError before any decode.  So does the product."""
+    with pytest.raises(ValueError):
+        pr.Schema(bad)
+
+
+def test_valid_names_still_parse_and_a_repeated_json_key_takes_the_last_value():
+    s = pr.Schema(_rec('{"name":"_x9","type":{"type":"enum","name":"ns.sub.E","symbols":["A","_b","C9"]}}', name="a.b.T"))
+    assert s.is_supported and s.arrow_schema.field("_x9").type == pa.utf8()
+    assert pr.Schema(_rec('{"name":"a","type":"int"}', name=".T")).is_supported          # an empty namespace in front of the dot
+    # serde_json's Map::insert: the later "logicalType" replaces the earlier one
+    s = pr.Schema(_rec('{"name":"t","type":{"type":"long","logicalType":"long","logicalType":"timestamp-micros"}}'))
+    assert s.arrow_schema.field("t").type == pa.timestamp("us")
+    # an "aliases" array holding anything but strings is no aliases at all (collected into an Option), not an error
+    s = pr.Schema('{"type":"record","name":"T","fields":[{"name":"r","type":{"type":"record","name":"R","aliases":["a",5],'
+                  '"fields":[{"name":"x","type":"int"}]}}]}')
+    assert s.is_supported and not (s.arrow_schema.field("r").metadata or {}).get(b"avro::aliases")
+
+
+@pytest.mark.parametrize("attrs,fixed", [('"precision":4,"scale":"x"', False), ('"precision":2,"scale":3', False), ('', False),
+                                         ('"precision":-2', True), ('"precision":2.0', False), ('"precision":0', True), ('"precision":"9"', False),
+                                         ('"precision":4,"scale":-1', True)])
+def test_invalid_decimal_metadata_falls_back_to_the_underlying_type(attrs, fixed):
+    """apache-avro ignores an invalid decimal annotation with a warning ("Ignoring invalid decimal logical type") — the
+    schema is then plain bytes / fixed; it neither fails nor guesses a scale.  Both restatements of the wider subset agree."""
+    comma = "," if attrs else ""
+    t = ('{"type":"fixed","name":"F","size":4,"logicalType":"decimal"%s%s}' if fixed else '{"type":"bytes","logicalType":"decimal"%s%s}') % (comma, attrs)
+    sj = _rec('{"name":"d","type":%s}' % t)
+    s = pr.Schema(sj)
+    assert s.is_supported and s.arrow_schema.field("d").type == (pa.binary(4) if fixed else pa.binary())
+    assert po.to_arrow_schema(po.parse_schema(sj, wide=True)).field("d").type == s.arrow_schema.field("d").type
+    ok = pr.Schema(_rec('{"name":"d","type":{"type":"bytes","logicalType":"decimal","precision":9}}'))
+    assert ok.arrow_schema.field("d").type == pa.decimal128(9, 0)                         # only "scale" may be absent
+
+
 def test_documented_limits_are_errors_not_crashes():
     deep = "int"
     for _ in range(5):
