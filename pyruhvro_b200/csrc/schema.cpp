@@ -1,6 +1,7 @@
 // See schema.hpp for the reference lines each function mirrors.
 #include "schema.hpp"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -105,12 +106,6 @@ void read_doc_aliases(const Json& j, const std::string& ns, AvroNode* n) {
     }
 }
 
-int json_int(const Json* j, int dflt) {
-    if (!j) return dflt;
-    if (j->kind == Json::Number) return int(std::strtol(j->str.c_str(), nullptr, 10));
-    return dflt;
-}
-
 // "precision" / "scale" of a decimal as apache-avro reads them (parse_json_integer_for_decimal): a JSON number that is a
 // non-negative integer ("4", not "4.0", "-4" or "4e0").  -1: anything else.
 long long decimal_meta(const Json* j) {
@@ -178,7 +173,10 @@ std::unique_ptr<AvroNode> primitive(const std::string& t, const Json* obj, const
 // Key used for the "unions may not contain duplicate types" rule.
 std::string union_key(const AvroNode& n) {
     switch (n.k) {
-        case AK::Record: case AK::Enum: case AK::Fixed: case AK::DecimalFixed: return "named:" + n.fullname;
+        // (UnionSchema::new checks kinds that are not named — record / enum / fixed / a reference may repeat, even under one
+        // name — and a decimal is a kind of its own whatever it sits on)
+        case AK::Record: case AK::Enum: case AK::Fixed: return std::string();
+        case AK::DecimalFixed: case AK::DecimalBytes: return "kind:decimal";
         case AK::Unsupported: return "unsupported:" + n.what;
         default: return "kind:" + std::to_string(int(n.k));
     }
@@ -200,7 +198,8 @@ std::unique_ptr<AvroNode> parse_node(const Json& j, const std::string& ns, int d
         for (auto& v : j.arr) {
             auto c = parse_node(v, ns, depth + 1, names);
             if (c->k == AK::Union) bad("unions may not immediately contain other unions");
-            if (!seen.insert(union_key(*c)).second) bad("unions cannot contain duplicate types");
+            const std::string key = union_key(*c);
+            if (!key.empty() && !seen.insert(key).second) bad("unions cannot contain duplicate types");
             u->sub.push_back(std::move(c));
         }
         if (u->sub.empty()) bad("empty union");
@@ -260,14 +259,19 @@ std::unique_ptr<AvroNode> parse_node(const Json& j, const std::string& ns, int d
                 if (earlier == s.str) bad("duplicate enum symbol \"" + s.str + "\"");   // Error::EnumSymbolDuplicate
             e->symbols.push_back(s.str);
         }
+        if (const Json* d = j.find("default")) {   // Error::EnumDefaultWrongType / Error::GetEnumDefault
+            if (!d->is_string()) bad("enum default must be a string");
+            if (std::find(e->symbols.begin(), e->symbols.end(), d->str) == e->symbols.end()) bad("enum default \"" + d->str + "\" is not one of the symbols");
+        }
         names.done[e->fullname] = e.get();
         return e;
     }
     if (ts == "fixed") {
         std::string fullname, fns;
         resolve_name(j, ns, &fullname, &fns);
-        const int size = json_int(j.find("size"), -1);
-        if (size < 0) bad("fixed without a non-negative \"size\"");
+        const long long size_ll = decimal_meta(j.find("size"));   // a JSON number that is a non-negative integer (as_u64)
+        if (size_ll < 0) bad("fixed without a non-negative \"size\"");
+        const int size = int(size_ll);
         std::string lt;
         if (const Json* l = j.find("logicalType"); l && l->is_string()) lt = l->str;
         std::unique_ptr<AvroNode> f;

@@ -178,6 +178,23 @@ def test_invalid_decimal_metadata_falls_back_to_the_underlying_type(attrs, fixed
     assert ok.arrow_schema.field("d").type == pa.decimal128(9, 0)                         # only "scale" may be absent
 
 
+def test_union_duplicates_fixed_size_and_enum_default_follow_the_library():
+    """UnionSchema::new only checks kinds that are not named (a record may repeat, two decimals may not); a fixed's size is a
+    JSON number that is a non-negative integer; an enum's default is one of its symbols."""
+    a = '{"type":"record","name":"A","fields":[{"name":"x","type":"int"}]}'
+    assert pr.Schema(_rec('{"name":"a","type":%s},{"name":"u","type":["null","A","A"]}' % a)).is_supported
+    for bad in [_rec('{"name":"u","type":[{"type":"bytes","logicalType":"decimal","precision":4},'
+                     '{"type":"fixed","name":"F","size":4,"logicalType":"decimal","precision":4}]}'),
+                _rec('{"name":"u","type":["int","int"]}'), _rec('{"name":"f","type":{"type":"fixed","name":"F","size":4.5}}'),
+                _rec('{"name":"f","type":{"type":"fixed","name":"F","size":"4"}}'),
+                _rec('{"name":"e","type":{"type":"enum","name":"E","symbols":["A","B"],"default":"C"}}'),
+                _rec('{"name":"e","type":{"type":"enum","name":"E","symbols":["A","B"],"default":5}}')]:
+        with pytest.raises(ValueError):
+            pr.Schema(bad)
+    assert pr.Schema(_rec('{"name":"e","type":{"type":"enum","name":"E","symbols":["A","B"],"default":"B"}}')).is_supported
+    assert pr.Schema(_rec('{"name":"u","type":["int",{"type":"int","logicalType":"date"}]}')).is_supported     # distinct kinds
+
+
 def test_documented_limits_are_errors_not_crashes():
     deep = "int"
     for _ in range(5):
