@@ -86,8 +86,8 @@ def _name(j: dict, enclosing_ns: Optional[str]):
 
 
 def _fix_aliases(aliases, ns):
-    if aliases is None:
-        return None
+    if not isinstance(aliases, list) or not all(isinstance(a, str) for a in aliases):
+        return None   # (apache-avro collects the aliases into an Option: anything but an array of strings is no aliases)
     return [a if ("." in a or not ns) else f"{ns}.{a}" for a in aliases]
 
 
