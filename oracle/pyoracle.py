@@ -80,7 +80,9 @@ def _name(j: dict, enclosing_ns: Optional[str]):
     if "." in name:
         ns, _, short = name.rpartition(".")
     else:
-        ns, short = j.get("namespace", enclosing_ns), name
+        ns, short = j.get("namespace"), name
+        if not isinstance(ns, str):     # (only a string is a namespace; anything else is as good as absent)
+            ns = enclosing_ns
     ns = ns or None
     return (f"{ns}.{short}" if ns else short), ns
 

@@ -102,28 +102,31 @@ def mutate_tree(rng, doc):
         for q in path[:-1]:
             x = x[q]
         return x
+
+    def fresh(v):   # (never a shared object: later mutations write into what they find)
+        return json.loads(json.dumps(v))
     for _ in range(rng.choice([1, 1, 2, 3])):
         acc = []
         nodes(doc, acc)
         path, x = rng.choice(acc)
         op = rng.randrange(7)
         if op == 0 and path:
-            parent(path)[path[-1]] = rng.choice(TREE_VALUES)
+            parent(path)[path[-1]] = fresh(rng.choice(TREE_VALUES))
         elif op == 1 and isinstance(x, dict) and x:
             del x[rng.choice(list(x))]
         elif op == 2 and isinstance(x, dict):
-            x[rng.choice(TREE_KEYS)] = rng.choice(TREE_VALUES)
+            x[rng.choice(TREE_KEYS)] = fresh(rng.choice(TREE_VALUES))
         elif op == 3 and isinstance(x, list) and x:
             if rng.random() < 0.5:
                 del x[rng.randrange(len(x))]
             else:
-                x.insert(rng.randrange(len(x) + 1), rng.choice(TREE_VALUES))
+                x.insert(rng.randrange(len(x) + 1), fresh(rng.choice(TREE_VALUES)))
         elif op == 4 and isinstance(x, list) and len(x) > 1:
-            x.append(json.loads(json.dumps(x[rng.randrange(len(x))])))
+            x.append(fresh(x[rng.randrange(len(x))]))
         elif op == 5 and isinstance(x, str) and path:
             parent(path)[path[-1]] = rng.choice([x + "x", x[:-1], x.upper(), "." + x, x + ".", "ns." + x])
         elif op == 6 and path:
-            parent(path)[path[-1]] = json.loads(json.dumps(rng.choice(acc)[1]))
+            parent(path)[path[-1]] = fresh(rng.choice(acc)[1])
     return doc
 
 
