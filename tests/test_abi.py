@@ -195,6 +195,29 @@ def test_union_duplicates_fixed_size_and_enum_default_follow_the_library():
     assert pr.Schema(_rec('{"name":"u","type":["int",{"type":"int","logicalType":"date"}]}')).is_supported     # distinct kinds
 
 
+def test_every_schema_literal_in_the_reference_tree_parses():
+    """The stricter front-end must not turn away anything the reference itself uses: every `r#"{...}"#` schema in its Rust
+    sources goes through rv_schema_parse.  (Skipped where /root/reference is absent: the GPU box.)"""
+    import glob
+    import re
+    files = glob.glob("/root/reference/**/*.rs", recursive=True)
+    if not files:
+        pytest.skip("/root/reference is not present")
+    n = 0
+    for f in files:
+        for m in re.finditer(r'r#"(.*?)"#', open(f, errors="ignore").read(), re.S):
+            body = m.group(1).strip()
+            if not body.startswith("{") or '"type"' not in body:
+                continue
+            try:
+                json.loads(body)
+            except ValueError:
+                continue
+            pr.Schema(body)
+            n += 1
+    assert n >= 30
+
+
 def test_documented_limits_are_errors_not_crashes():
     deep = "int"
     for _ in range(5):
