@@ -179,12 +179,12 @@ def test_invalid_decimal_metadata_falls_back_to_the_underlying_type(attrs, fixed
 
 
 def test_union_duplicates_fixed_size_and_enum_default_follow_the_library():
-    """UnionSchema::new only checks kinds that are not named (a record may repeat, two decimals may not); a fixed's size is a
+    """UnionSchema::new only checks kinds that are not named (a record may repeat, two decimals on bytes may not); a fixed's size is a
     JSON number that is a non-negative integer; an enum's default is one of its symbols."""
     a = '{"type":"record","name":"A","fields":[{"name":"x","type":"int"}]}'
     assert pr.Schema(_rec('{"name":"a","type":%s},{"name":"u","type":["null","A","A"]}' % a)).is_supported
     for bad in [_rec('{"name":"u","type":[{"type":"bytes","logicalType":"decimal","precision":4},'
-                     '{"type":"fixed","name":"F","size":4,"logicalType":"decimal","precision":4}]}'),
+                     '{"type":"bytes","logicalType":"decimal","precision":9}]}'),
                 _rec('{"name":"u","type":["int","int"]}'), _rec('{"name":"f","type":{"type":"fixed","name":"F","size":4.5}}'),
                 _rec('{"name":"f","type":{"type":"fixed","name":"F","size":"4"}}'),
                 _rec('{"name":"e","type":{"type":"enum","name":"E","symbols":["A","B"],"default":"C"}}'),
