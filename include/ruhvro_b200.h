@@ -56,7 +56,11 @@ typedef enum rv_status {
 /* ---- schema --------------------------------------------------------------------------- */
 
 /* Replaces ruhvro::deserialize::parse_schema (ruhvro/src/deserialize.rs:18-20).  Parsing an
- * unsupported-but-valid schema succeeds; use rv_schema_is_supported() for the gate. */
+ * unsupported-but-valid schema succeeds; use rv_schema_is_supported() for the gate.  A document
+ * apache-avro's Schema::parse_str turns away is RV_ERR_SCHEMA here too: malformed JSON, missing
+ * attributes, type / field names and enum symbols outside [A-Za-z_][A-Za-z0-9_]*, repeated field
+ * names or enum symbols, duplicate unnamed kinds or a nested union in a union.  (Not checked:
+ * record field defaults against the field's type.) */
 rv_status rv_schema_parse(const char* json, size_t len, rv_schema** out);
 rv_schema* rv_schema_retain(rv_schema* s);  /* Arc::clone (deserialize.rs:96) */
 void rv_schema_release(rv_schema* s);
