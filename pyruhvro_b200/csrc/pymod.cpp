@@ -58,12 +58,20 @@ bool pack_list(PyObject* list, Alloc alloc, Packed* out) {
     const unsigned hw = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
     // One read of every element's header: type check, payload pointer, size (left in offsets[i + 1]).  Long lists are
     // walked by several threads — the calling thread holds the GIL throughout, so nothing they read can change.
-    auto walk = [list, offsets, p = ptrs.get()](Py_ssize_t a, Py_ssize_t b) -> Py_ssize_t {  // -> first non-bytes element, or b
+    auto walk = [list, offsets, p = ptrs.get()](Py_ssize_t a, Py_ssize_t b) -> Py_ssize_t {  // -> first element that is neither bytes nor bytearray, or b
         for (Py_ssize_t i = a; i < b; ++i) {
             PyObject* item = PyList_GET_ITEM(list, i);
-            if (!PyBytes_Check(item)) return i;
-            p[static_cast<size_t>(i)] = PyBytes_AS_STRING(item);
-            offsets[i + 1] = static_cast<int64_t>(PyBytes_GET_SIZE(item));
+            if (PyBytes_Check(item)) {
+                p[static_cast<size_t>(i)] = PyBytes_AS_STRING(item);
+                offsets[i + 1] = static_cast<int64_t>(PyBytes_GET_SIZE(item));
+            } else if (PyByteArray_Check(item)) {
+                // PyBackedBytes (what the reference extracts, src/lib.rs:29-33) takes `bytes` or `bytearray`.  The payload is
+                // copied below while this call still holds the GIL, so the array cannot change size meanwhile.
+                p[static_cast<size_t>(i)] = PyByteArray_AS_STRING(item);
+                offsets[i + 1] = static_cast<int64_t>(PyByteArray_GET_SIZE(item));
+            } else {
+                return i;
+            }
         }
         return b;
     };
@@ -82,7 +90,7 @@ bool pack_list(PyObject* list, Alloc alloc, Packed* out) {
         for (unsigned w = hw; w-- > 0;) if (stop[w] >= 0) bad = stop[w];   // the lowest failing index wins
     }
     if (bad < n) {
-        PyErr_Format(PyExc_TypeError, "argument 'list': element %zd is '%s', expected 'bytes'", bad, Py_TYPE(PyList_GET_ITEM(list, bad))->tp_name);
+        PyErr_Format(PyExc_TypeError, "argument 'list': element %zd is '%s', expected 'bytes' or 'bytearray'", bad, Py_TYPE(PyList_GET_ITEM(list, bad))->tp_name);
         return false;
     }
     for (Py_ssize_t i = 0; i < n; ++i) offsets[i + 1] += offsets[i];

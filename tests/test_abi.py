@@ -340,6 +340,16 @@ def test_list_packing_matches_binaryarray_from_vec():
         ext.pack(long)
     with pytest.raises(TypeError):
         ext.pack((b"a",))                                              # a list, like PyO3's Vec<Bound<PyBytes>> extraction
+    # PyBackedBytes (src/lib.rs:29-33) extracts from `bytes` (subclasses included) and from `bytearray`, nothing else
+    class MyBytes(bytes):
+        pass
+    mixed = [bytearray(b"ab"), MyBytes(b"c"), bytearray(), b"de"]
+    data, offs = ext.pack(mixed)
+    assert data == b"abcde" and list(np.frombuffer(offs, dtype=np.int64)) == [0, 2, 3, 3, 5]
+    many = [bytearray([i & 255]) * (i % 5) if i % 3 else bytes([i & 255]) * (i % 5) for i in range(150_000)]   # the threaded walk
+    assert ext.pack(many)[0] == b"".join(bytes(x) for x in many)
+    with pytest.raises(TypeError, match="element 0 is 'memoryview', expected 'bytes' or 'bytearray'"):
+        ext.pack([memoryview(b"ab")])
 
 
 def test_framed_entry_points_validate_before_touching_the_gpu():
