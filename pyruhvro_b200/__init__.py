@@ -8,7 +8,7 @@ Python surface mirrored from the reference's PyO3 module (``/root/reference/src/
     serialize_record_batch(batch, schema, num_chunks)        -> list[pyarrow.Array]        (:91-106)
     serialize_record_batch_spawn(batch, schema, num_chunks)  -> list[pyarrow.Array]        (:130-147)
 
-Same argument meaning and error behaviour: elements of ``list`` must be ``bytes``; every failure is
+Same argument meaning and error behaviour: elements of ``list`` must be ``bytes`` or ``bytearray`` (PyBackedBytes); every failure is
 a ``ValueError`` carrying the native message (:25-27); the GIL is released around the native work
 (:64-69); parsed schemas are cached by their source string for the life of the process (:39-54);
 batches cross into pyarrow through the Arrow C Data Interface, zero-copy (:70,88).
