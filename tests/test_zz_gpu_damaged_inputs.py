@@ -83,3 +83,11 @@ def test_damaged_batches(coracle):
     finally:
         pr.set_jit_enabled(-1)
     assert seen["decoded"] > 10 and seen["error"] > 10
+
+
+def test_bytearray_elements_decode_like_bytes(coracle):
+    """PyBackedBytes (src/lib.rs:29-33) takes `bytes` or `bytearray` elements; both gather into the same packed buffer."""
+    from tests.parity import assert_matches_oracle, gen_case
+    sj, recs, data, off = gen_case(7, n=300)
+    mixed = [bytearray(r) if i % 2 else r for i, r in enumerate(recs)]
+    assert_matches_oracle(coracle, pr.deserialize_array_threaded(mixed, sj, 3), sj, data, off, len(recs), 3)
