@@ -770,7 +770,10 @@ static void *worker(void *arg) {
 int64_t orc_decode_threaded(const orc_schema *s, const uint8_t *data, const int64_t *offsets, int64_t n,
                             int64_t num_chunks, int threads, orc_batch **out) {
     int64_t k = orc_clamp_chunks(num_chunks, n);
-    job j = { s, data, offsets, n, k, 0, PTHREAD_MUTEX_INITIALIZER, out, 0 };
+    job j;
+    memset(&j, 0, sizeof j);
+    j.s = s; j.data = data; j.offsets = offsets; j.n = n; j.k = k; j.out = out;
+    pthread_mutex_init(&j.mu, NULL);
     CPU_ZERO(&j.allowed);
     j.n_allowed = 0;
     if (g_pin && sched_getaffinity(0, sizeof j.allowed, &j.allowed) == 0) j.n_allowed = CPU_COUNT(&j.allowed);
