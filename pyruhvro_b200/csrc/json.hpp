@@ -79,7 +79,11 @@ class JsonReader {
             if (p_ >= end_) fail("unterminated string");
             char c = *p_++;
             if (c == '"') return out;
-            if (c != '\\') { out.push_back(c); continue; }
+            if (c != '\\') {
+                if (static_cast<unsigned char>(c) < 0x20) fail("control character in a string");   // (as serde_json: must be escaped)
+                out.push_back(c);
+                continue;
+            }
             if (p_ >= end_) fail("unterminated escape");
             c = *p_++;
             switch (c) {
