@@ -88,3 +88,48 @@ def test_gather_two_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] == "ok" for r in results), results
+
+
+def test_plan_grouping_invariants_through_the_c_abi():
+    """rv_gather_plan on synthetic per-rank counts (host-only: no CUDA behind it): ranks map to consecutive groups, no
+    group exceeds Arrow's i32 ceiling in any row space / stream, the grouping is greedy-minimal (the next rank would not
+    have fitted), and a rank that is beyond the ceiling on its own is RV_ERR_OVERFLOW."""
+    import ctypes
+    import pyruhvro_b200 as pr
+    from tests import emu
+    L = pr.lib
+    L.rv_gather_meta_len.restype = ctypes.c_int64
+    L.rv_gather_meta_len.argtypes = [ctypes.c_void_p]
+    L.rv_gather_plan.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    L.rv_gather_num_groups.argtypes = [ctypes.c_void_p]
+    L.rv_gather_group_of_rank.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.rv_gather_free.argtypes = [ctypes.c_void_p]
+    lim, multi, rejected = 2**31 - 1, 0, 0
+    for seed in range(400):
+        rng = random.Random(seed)
+        sj, recs, data, off = gen_case(seed % 40, n=200)
+        s = pr._get_or_parse_schema(sj)
+        m = emu.Shard(sj, data, off, len(recs)).meta().astype(np.int64)
+        assert len(m) == L.rv_gather_meta_len(s.handle)
+        world = rng.choice([1, 2, 3, 4, 8, 16])
+        metas = np.ascontiguousarray(np.stack([m * rng.choice([0, 1, 1000, 20000, 50000, 100000, 200000, 400000, 800000]) for _ in range(world)]))
+        g = ctypes.c_void_p()
+        rc = L.rv_gather_plan(s.handle, metas.ctypes.data, world, ctypes.byref(g))
+        oversized = any((metas[r] > lim).any() for r in range(world))
+        assert (rc != 0) == oversized, (seed, rc, pr._last_error())
+        if rc:
+            assert rc == 8 and "i32" in pr._last_error()      # RV_ERR_OVERFLOW
+            rejected += 1
+            continue
+        try:
+            ng = L.rv_gather_num_groups(g)
+            gor = [L.rv_gather_group_of_rank(g, r) for r in range(world)]
+            assert gor[0] == 0 and gor[-1] == ng - 1 and all(b - a in (0, 1) for a, b in zip(gor, gor[1:])), gor
+            sums = [metas[[r for r in range(world) if gor[r] == k]].sum(axis=0) for k in range(ng)]
+            assert not any((t > lim).any() for t in sums)
+            for k in range(ng - 1):
+                assert ((sums[k] + metas[gor.index(k + 1)]) > lim).any(), (seed, gor)
+            multi += ng > 1
+        finally:
+            L.rv_gather_free(g)
+    assert multi > 20 and rejected > 20
